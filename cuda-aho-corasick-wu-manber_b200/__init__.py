@@ -1,0 +1,225 @@
+"""B200-native Aho-Corasick / Wu-Manber multi-pattern scan -- host-side Python layer.
+
+Everything here is a thin ctypes binding over the C ABI of ``libacwm_b200.so``
+(``include/acwm.h``); the scan itself runs only in the hand-written sm_100a kernels of
+``csrc/``.  There is no CPU search path: if the shared library is missing, importing
+this package raises.
+
+    from acwm_pkg import load; acwm = load()
+    mt = acwm.Matcher(acwm.AC, patterns, alphabet=4)          # preproc_ac equivalent
+    count, positions = mt.search_host(text)                   # search_ac equivalent (+ positions)
+
+Reference-shaped functions (same names / arguments as smatcher.h) are in
+``.smatcher``; the multi-GPU sharding layer in ``.sharding``; synthetic data in
+``.datagen``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libacwm_b200.so")
+
+AC, WM = 0, 1
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_OVERFLOW, ERR_BAD_TEXT = range(7)
+
+BLOB_FRONT, BLOB_FILTER2, BLOB_BUCKET_START, BLOB_ENTRIES, BLOB_PATTERNS, BLOB_PARAMS, BLOB_SYMCLASS = range(7)
+
+
+class AcwmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"acwm error {code}: {msg}")
+        self.code = code
+
+
+class Options(C.Structure):
+    _fields_ = [("smem_table_budget", C.c_uint32), ("force_stride", C.c_uint32), ("force_depth", C.c_uint32),
+                ("force_bytes_path", C.c_uint32), ("force_threads", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("algo", "alphabet", "n_patterns", "n_distinct", "m_min", "m_max", "packed2bit", "stride", "depth",
+                 "exact_front", "n_states", "n_rows", "table_in_smem", "smem_bytes")] + \
+               [("table_bytes", C.c_uint64), ("threads", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+class ScanParams(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("algo", "packed2bit", "alphabet", "m_min", "m_max", "stride", "depth", "exact_front", "n_rows",
+                 "f1_sh1", "f1_mult", "f1_sh2", "f1_words", "b2", "f2_mult", "f2_sh", "f2_words", "hb_mult",
+                 "hb_sh", "n_buckets", "n_entries", "n_classes")] + [("reserved", C.c_uint32 * 8)]
+
+
+VENTRY_DTYPE = np.dtype([("key", "<u4"), ("len", "<u4"), ("offset", "<u8")])
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.acwm_last_error.restype = C.c_char_p
+        L.acwm_build.argtypes = [C.c_int, _u8p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Options),
+                                 C.POINTER(C.c_void_p)]
+        L.acwm_upload.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.acwm_scan_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        L.acwm_fetch.argtypes = [C.c_void_p, _u64p, C.c_void_p, C.c_uint64, _u64p, C.c_void_p]
+        L.acwm_result_device_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.acwm_search_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p, C.c_void_p, C.c_uint64, _u64p]
+        L.acwm_last_kernel_seconds.restype = C.c_double
+        L.acwm_last_kernel_seconds.argtypes = [C.c_void_p]
+        L.acwm_launch_count.restype = C.c_ulonglong
+        L.acwm_launch_count.argtypes = [C.c_void_p]
+        L.acwm_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+        L.acwm_free.argtypes = [C.c_void_p]
+        L.acwm_free.restype = None
+        L.acwm_shard_bounds.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u64p]
+        L.acwm_shard_bounds.restype = None
+        L.acwm_table_blob.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _u64p]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, allow=()):
+    if rc != OK and rc not in allow:
+        raise AcwmError(rc, lib().acwm_last_error().decode())
+    return rc
+
+
+def flatten_patterns(patterns):
+    """(p, m) uint8 array, or a list of uint8 arrays of any lengths -> (flat, lens|None, m, p)."""
+    if isinstance(patterns, np.ndarray) and patterns.ndim == 2:
+        pats = np.ascontiguousarray(patterns, dtype=np.uint8)
+        return pats.reshape(-1), None, pats.shape[1], pats.shape[0]
+    arrs = [np.ascontiguousarray(x, dtype=np.uint8).reshape(-1) for x in patterns]
+    lens = np.array([a.size for a in arrs], dtype=np.uint32)
+    flat = np.concatenate(arrs) if arrs else np.zeros(0, np.uint8)
+    return flat, lens, 0, len(arrs)
+
+
+def shard_bounds(n: int, world: int, rank: int, halo: int):
+    """Shard geometry of main.c:467-477 (see acwm_shard_bounds)."""
+    s, l = C.c_uint64(), C.c_uint64()
+    lib().acwm_shard_bounds(n, world, rank, halo, C.byref(s), C.byref(l))
+    return int(s.value), int(l.value)
+
+
+class Matcher:
+    """A compiled pattern set (``acwm_matcher``).  algo = AC or WM."""
+
+    def __init__(self, algo: int, patterns, alphabet: int, **opts):
+        flat, lens, m, p = flatten_patterns(patterns)
+        o = Options()
+        for k, v in opts.items():
+            setattr(o, k, int(v))
+        h = C.c_void_p()
+        keep = flat if flat.size else np.zeros(1, np.uint8)
+        _check(lib().acwm_build(algo, keep.ctypes.data_as(_u8p),
+                                None if lens is None else lens.ctypes.data_as(_u32p), m, p, alphabet,
+                                C.byref(o), C.byref(h)))
+        self._h = h
+        self.algo = algo
+
+    # ---- lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().acwm_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def info(self) -> dict:
+        i = Info()
+        _check(lib().acwm_get_info(self._h, C.byref(i)))
+        return i.as_dict()
+
+    def blob(self, which: int) -> np.ndarray:
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        _check(lib().acwm_table_blob(self._h, which, C.byref(ptr), C.byref(nbytes)))
+        if nbytes.value == 0:
+            return np.zeros(0, np.uint8)
+        buf = (C.c_uint8 * nbytes.value).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.uint8).copy()
+
+    def params(self) -> ScanParams:
+        return ScanParams.from_buffer_copy(self.blob(BLOB_PARAMS).tobytes())
+
+    # ---- device
+    def upload(self, device: int = -1, pos_capacity: int = 0):
+        _check(lib().acwm_upload(self._h, device, pos_capacity))
+        return self
+
+    def scan_device(self, d_text_ptr: int, n: int, want_positions: bool = True, stream: int = 0,
+                    report_from: int = 0):
+        """Asynchronous scan of device-resident text (raw pointer + length)."""
+        _check(lib().acwm_scan_device(self._h, C.c_void_p(d_text_ptr), n, report_from, int(want_positions),
+                                      C.c_void_p(stream)))
+
+    def scan_tensor(self, text, want_positions: bool = True, report_from: int = 0):
+        """Scan a CUDA uint8 torch tensor on torch's current stream."""
+        import torch
+        assert text.is_cuda and text.dtype == torch.uint8 and text.is_contiguous()
+        st = torch.cuda.current_stream(text.device).cuda_stream
+        self.scan_device(text.data_ptr(), text.numel(), want_positions, st, report_from)
+
+    def fetch(self, cap: int = 0, stream: int = 0, allow_overflow: bool = False):
+        count, nw = C.c_uint64(), C.c_uint64()
+        pos = np.empty(max(cap, 1), np.uint64)
+        rc = _check(lib().acwm_fetch(self._h, C.byref(count), pos.ctypes.data_as(C.c_void_p) if cap else None, cap,
+                                     C.byref(nw), C.c_void_p(stream)),
+                    allow=(ERR_OVERFLOW,) if allow_overflow else ())
+        return int(count.value), pos[:int(nw.value)], rc
+
+    def result_device_ptrs(self):
+        c, p = C.c_void_p(), C.c_void_p()
+        _check(lib().acwm_result_device_ptrs(self._h, C.byref(c), C.byref(p)))
+        return c.value, p.value
+
+    # ---- host text, end to end
+    def search_host(self, text, cap: int | None = None, want_positions: bool = True, allow_overflow: bool = False):
+        """text: numpy uint8 array (or anything exposing a host pointer via ``data_ptr``/``ctypes``)."""
+        if hasattr(text, "data_ptr"):  # pinned torch tensor
+            ptr, n = text.data_ptr(), text.numel()
+        else:
+            text = np.ascontiguousarray(text, dtype=np.uint8)
+            ptr, n = text.ctypes.data, text.size
+        count, nw = C.c_uint64(), C.c_uint64()
+        if want_positions:
+            cap = int(cap if cap is not None else max(1, n))
+            pos = np.empty(cap, np.uint64)
+            pptr = pos.ctypes.data_as(C.c_void_p)
+        else:
+            cap, pos, pptr = 0, np.zeros(0, np.uint64), None
+        rc = _check(lib().acwm_search_host(self._h, C.c_void_p(ptr), n, C.byref(count), pptr, cap, C.byref(nw)),
+                    allow=(ERR_OVERFLOW,) if allow_overflow else ())
+        self.last_rc = rc
+        return int(count.value), pos[:int(nw.value)]
+
+    @property
+    def last_kernel_seconds(self) -> float:
+        return float(lib().acwm_last_kernel_seconds(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().acwm_launch_count(self._h))

@@ -1,0 +1,446 @@
+// C ABI of libacwm_b200.so (see include/acwm.h): matcher handle, device residency,
+// scan launches, host<->device pipeline.  The reference-shaped shims live in shims.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "matcher.hpp"
+
+namespace acwm {
+
+cudaError_t launch_scan_packed(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st);
+cudaError_t launch_scan_bytes(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st);
+cudaError_t launch_finalize(uint32_t *tile_count, uint64_t n_tiles, unsigned long long *block_sums,
+		uint32_t max_blocks, const uint64_t *staging, uint64_t cap, uint32_t tile_syms, uint64_t data_lo,
+		uint64_t *positions, Control *ctl, int sm_count, cudaStream_t st);
+
+static thread_local std::string g_last_error;
+
+int set_error(int code, const std::string &msg) {
+	g_last_error = msg;
+	return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+	g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+	return ACWM_ERR_CUDA;
+}
+
+#define CU(call)                                  \
+	do {                                          \
+		cudaError_t e_ = (call);                  \
+		if (e_ != cudaSuccess)                    \
+			return cuda_fail(e_, #call);          \
+	} while (0)
+
+template <class T>
+static int dev_upload(T **dst, const void *src, size_t bytes) {
+	*dst = nullptr;
+	if (bytes == 0)
+		bytes = 16; // keep pointers valid
+	CU(cudaMalloc((void **) dst, (bytes + 15) & ~(size_t) 15));
+	if (src)
+		CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+	return ACWM_OK;
+}
+
+static int ensure_positions(acwm_matcher *mt, uint64_t cap) {
+	if (cap <= mt->pos_cap)
+		return ACWM_OK;
+	if (mt->d_staging)
+		cudaFree(mt->d_staging);
+	if (mt->d_positions)
+		cudaFree(mt->d_positions);
+	mt->d_staging = mt->d_positions = nullptr;
+	mt->pos_cap = 0;
+	CU(cudaMalloc((void **) &mt->d_staging, cap * 8));
+	CU(cudaMalloc((void **) &mt->d_positions, cap * 8));
+	mt->pos_cap = cap;
+	return ACWM_OK;
+}
+
+static int ensure_tiles(acwm_matcher *mt, uint64_t n_tiles) {
+	if (n_tiles <= mt->tile_cap)
+		return ACWM_OK;
+	if (mt->d_tile_count)
+		cudaFree(mt->d_tile_count);
+	mt->d_tile_count = nullptr;
+	mt->tile_cap = 0;
+	const uint64_t want = n_tiles + n_tiles / 8 + 1024;
+	CU(cudaMalloc((void **) &mt->d_tile_count, want * 4));
+	mt->tile_cap = want;
+	return ACWM_OK;
+}
+
+static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
+	if (device >= 0)
+		CU(cudaSetDevice(device));
+	CU(cudaGetDevice(&mt->device));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, mt->device));
+	if (prop.major < 10)
+		return set_error(ACWM_ERR_UNSUPPORTED, "libacwm_b200 is built for sm_100a (B200) only");
+	mt->sm_count = prop.multiProcessorCount;
+	mt->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
+	mt->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
+	const Compiled &c = mt->c;
+	int rc;
+	if ((rc = dev_upload(&mt->d_front, c.front.data(), c.front.size())))
+		return rc;
+	if ((rc = dev_upload(&mt->d_filter2, c.filter2.data(), c.filter2.size() * 4)))
+		return rc;
+	if ((rc = dev_upload(&mt->d_bucket_start, c.bucket_start.data(), c.bucket_start.size() * 4)))
+		return rc;
+	if ((rc = dev_upload(&mt->d_entries, c.entries.data(), c.entries.size() * sizeof(acwm_ventry))))
+		return rc;
+	if ((rc = dev_upload(&mt->d_patterns, mt->ps.bytes.data(), mt->ps.bytes.size())))
+		return rc;
+	CU(cudaMalloc((void **) &mt->d_ctl, sizeof(Control)));
+	CU(cudaMemset(mt->d_ctl, 0, sizeof(Control)));
+	CU(cudaMallocHost((void **) &mt->h_ctl, sizeof(Control)));
+	CU(cudaMalloc((void **) &mt->d_block_sums, kMaxScanBlocks * sizeof(unsigned long long)));
+	CU(cudaStreamCreateWithFlags(&mt->s_copy, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&mt->s_scan, cudaStreamNonBlocking));
+	for (auto &e : mt->ev_copy)
+		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	// a front table that lives in global memory is kept L2-resident with an access-policy window
+	if (!c.info.table_in_smem && mt->l2_persist_max) {
+		const size_t want = std::min(c.front.size(), mt->l2_persist_max);
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+		(void) cudaGetLastError();
+	}
+	mt->uploaded = true;
+	if (pos_capacity)
+		return ensure_positions(mt, pos_capacity);
+	return ACWM_OK;
+}
+
+static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
+	if (mt->c.info.table_in_smem || !mt->l2_window_max)
+		return;
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof(v));
+	v.accessPolicyWindow.base_ptr = mt->d_front;
+	v.accessPolicyWindow.num_bytes = std::min(mt->c.front.size(), mt->l2_window_max);
+	v.accessPolicyWindow.hitRatio = 1.0f;
+	v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+	(void) cudaGetLastError();
+}
+
+// Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes).
+static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
+		uint64_t tile_hi, int want_positions, cudaStream_t st) {
+	const Compiled &c = mt->c;
+	ScanArgs a;
+	memset(&a, 0, sizeof(a));
+	const uint64_t mis = (uint64_t) (uintptr_t) d_text & 15u;
+	a.text16 = d_text - mis;
+	a.data_lo = mis;
+	a.data_hi = mis + n;
+	a.report_lo = mis + std::max<uint64_t>(c.prm.m_min - 1, report_from);
+	a.tile_lo = tile_lo;
+	a.tile_hi = tile_hi;
+	a.front = mt->d_front;
+	a.front_bytes = (uint32_t) c.front.size();
+	a.front_in_smem = c.info.table_in_smem;
+	a.filter2 = mt->d_filter2;
+	a.bucket_start = mt->d_bucket_start;
+	a.entries = mt->d_entries;
+	a.patterns = mt->d_patterns;
+	a.prm = c.prm;
+	a.ctl = mt->d_ctl;
+	a.staging = mt->d_staging;
+	a.cap = want_positions ? mt->pos_cap : 0;
+	a.tile_count = mt->d_tile_count;
+	a.want_positions = want_positions;
+	const uint32_t threads = c.info.threads, warps = threads / 32;
+	const uint64_t ntl = tile_hi - tile_lo;
+	const uint32_t grid = (uint32_t) std::min<uint64_t>((uint64_t) mt->sm_count, (ntl + warps - 1) / warps);
+	if (grid == 0)
+		return ACWM_OK;
+	cudaError_t e = c.prm.packed2bit ? launch_scan_packed(a, threads, c.info.smem_bytes, grid, st)
+									 : launch_scan_bytes(a, threads, c.info.smem_bytes, grid, st);
+	if (e != cudaSuccess)
+		return cuda_fail(e, "scan kernel launch");
+	mt->launches++;
+	return ACWM_OK;
+}
+
+static uint32_t tile_syms(const acwm_matcher *mt) { return mt->c.prm.packed2bit ? kWarpTile : kWarpTileB; }
+
+static int finalize_positions(acwm_matcher *mt, uint64_t n_tiles, uint64_t data_lo, cudaStream_t st) {
+	cudaError_t e = launch_finalize(mt->d_tile_count, n_tiles, mt->d_block_sums, kMaxScanBlocks, mt->d_staging,
+			mt->pos_cap, tile_syms(mt), data_lo, mt->d_positions, mt->d_ctl, mt->sm_count, st);
+	if (e != cudaSuccess)
+		return cuda_fail(e, "finalize launch");
+	mt->launches += 2;
+	return ACWM_OK;
+}
+
+} // namespace acwm
+
+using namespace acwm;
+
+extern "C" {
+
+const char *acwm_last_error(void) { return g_last_error.c_str(); }
+
+int acwm_build(int algo, const uint8_t *patterns, const uint32_t *lens, uint32_t m, uint32_t p, uint32_t alphabet,
+		const acwm_options *opts, acwm_matcher **out) {
+	if (!out)
+		return set_error(ACWM_ERR_INVALID, "out == NULL");
+	*out = nullptr;
+	acwm_matcher *mt = new (std::nothrow) acwm_matcher();
+	if (!mt)
+		return set_error(ACWM_ERR_NOMEM, "host allocation failed");
+	if (opts)
+		mt->opts = *opts;
+	std::string err;
+	int rc = normalize_patterns(patterns, lens, m, p, alphabet, mt->ps, err);
+	if (rc == ACWM_OK)
+		rc = compile_tables(algo, mt->ps, mt->opts, mt->c, err);
+	if (rc == ACWM_OK && mt->opts.force_threads) { // force_threads (tuning / tests)
+		const uint32_t t = mt->opts.force_threads;
+		const bool packed = mt->c.prm.packed2bit;
+		const uint32_t per_warp = packed ? kWarpSmemPacked : kWarpSmemBytes;
+		const uint32_t tables = mt->c.info.smem_bytes - (mt->c.info.threads / 32) * per_warp;
+		const bool ok = packed ? (t == 1024 || t == 768 || t == 512 || t == 256)
+							   : (t == 512 || t == 384 || t == 256 || t == 128);
+		if (!ok || tables + (t / 32) * per_warp > kMaxSmem) {
+			err = "forced thread count not available for this table size";
+			rc = ACWM_ERR_INVALID;
+		} else {
+			mt->c.info.threads = t;
+			mt->c.info.smem_bytes = tables + (t / 32) * per_warp;
+		}
+	}
+	if (rc != ACWM_OK) {
+		delete mt;
+		return set_error(rc, err);
+	}
+	*out = mt;
+	return ACWM_OK;
+}
+
+int acwm_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
+	if (!mt)
+		return set_error(ACWM_ERR_INVALID, "matcher == NULL");
+	if (mt->uploaded) {
+		if (device >= 0 && device != mt->device)
+			return set_error(ACWM_ERR_INVALID, "matcher already resident on another device");
+		CU(cudaSetDevice(mt->device));
+		return ensure_positions(mt, pos_capacity);
+	}
+	return do_upload(mt, device, pos_capacity);
+}
+
+int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, int want_positions,
+		void *stream) {
+	if (!mt || (!d_text && n))
+		return set_error(ACWM_ERR_INVALID, "NULL argument");
+	int rc;
+	if (!mt->uploaded && (rc = do_upload(mt, -1, 0)))
+		return rc;
+	if (want_positions && mt->pos_cap == 0)
+		return set_error(ACWM_ERR_INVALID, "positions requested but the matcher was uploaded with pos_capacity = 0");
+	cudaStream_t st = (cudaStream_t) stream;
+	const uint64_t mis = (uint64_t) (uintptr_t) d_text & 15u;
+	const uint64_t T = tile_syms(mt);
+	const uint64_t n_tiles = n ? (mis + n + T - 1) / T : 0;
+	if (want_positions && (rc = ensure_tiles(mt, n_tiles)))
+		return rc;
+	CU(cudaMemsetAsync(mt->d_ctl, 0, sizeof(Control), st));
+	apply_l2_window(mt, st);
+	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, st)))
+		return rc;
+	if (want_positions && n_tiles && (rc = finalize_positions(mt, n_tiles, mis, st)))
+		return rc;
+	mt->last_want_positions = want_positions;
+	return ACWM_OK;
+}
+
+int acwm_fetch(acwm_matcher *mt, uint64_t *count, uint64_t *positions, uint64_t cap, uint64_t *n_written,
+		void *stream) {
+	if (!mt || !mt->uploaded)
+		return set_error(ACWM_ERR_INVALID, "matcher not uploaded");
+	cudaStream_t st = (cudaStream_t) stream;
+	CU(cudaMemcpyAsync(mt->h_ctl, mt->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const Control &h = *mt->h_ctl;
+	if (count)
+		*count = h.count;
+	if (n_written)
+		*n_written = 0;
+	if (h.bad_text)
+		return set_error(ACWM_ERR_BAD_TEXT, "text holds a byte >= 4 but the matcher was built for alphabet <= 4");
+	if (positions && mt->last_want_positions) {
+		const uint64_t have = std::min<uint64_t>(h.written, mt->pos_cap);
+		const uint64_t w = std::min<uint64_t>(have, cap);
+		if (w)
+			CU(cudaMemcpy(positions, mt->d_positions, w * 8, cudaMemcpyDeviceToHost));
+		if (n_written)
+			*n_written = w;
+		if (h.cursor > mt->pos_cap || h.count > cap)
+			return set_error(ACWM_ERR_OVERFLOW, "more matches than position capacity");
+	}
+	return ACWM_OK;
+}
+
+int acwm_result_device_ptrs(acwm_matcher *mt, uint64_t **d_count, uint64_t **d_positions) {
+	if (!mt || !mt->uploaded)
+		return set_error(ACWM_ERR_INVALID, "matcher not uploaded");
+	if (d_count)
+		*d_count = reinterpret_cast<uint64_t *>(&mt->d_ctl->count);
+	if (d_positions)
+		*d_positions = mt->d_positions;
+	return ACWM_OK;
+}
+
+int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t *count, uint64_t *positions,
+		uint64_t cap, uint64_t *n_written) {
+	if (!mt || (!text && n))
+		return set_error(ACWM_ERR_INVALID, "NULL argument");
+	int rc;
+	if (!mt->uploaded && (rc = do_upload(mt, -1, 0)))
+		return rc;
+	CU(cudaSetDevice(mt->device));
+	const int want_positions = positions != nullptr && cap > 0;
+	if (want_positions && (rc = ensure_positions(mt, cap)))
+		return rc;
+	if (n + 64 > mt->text_cap) {
+		if (mt->d_text)
+			cudaFree(mt->d_text);
+		mt->d_text = nullptr;
+		mt->text_cap = 0;
+		CU(cudaMalloc((void **) &mt->d_text, n + 64));
+		mt->text_cap = n + 64;
+	}
+	const uint64_t T = tile_syms(mt);
+	const uint64_t n_tiles = n ? (n + T - 1) / T : 0;
+	if (want_positions && (rc = ensure_tiles(mt, n_tiles)))
+		return rc;
+	// chunks of ~32 MiB, whole tiles each: H2D on s_copy, scan on s_scan as soon as the chunk
+	// (and, through stream order, everything before it -- the halo) has landed
+	const uint64_t chunk_tiles = std::max<uint64_t>(1, (32ull << 20) / T);
+	const uint64_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+	while (mt->ev_time.size() < 2 * n_chunks + 2) {
+		cudaEvent_t e;
+		CU(cudaEventCreate(&e));
+		mt->ev_time.push_back(e);
+	}
+	CU(cudaMemsetAsync(mt->d_ctl, 0, sizeof(Control), mt->s_scan));
+	apply_l2_window(mt, mt->s_scan);
+	for (uint64_t ci = 0; ci < n_chunks; ci++) {
+		const uint64_t b0 = ci * chunk_tiles * T, b1 = std::min<uint64_t>(n, (ci + 1) * chunk_tiles * T);
+		CU(cudaMemcpyAsync(mt->d_text + b0, text + b0, b1 - b0, cudaMemcpyHostToDevice, mt->s_copy));
+		cudaEvent_t ev = mt->ev_copy[ci % mt->ev_copy.size()];
+		CU(cudaEventRecord(ev, mt->s_copy));
+		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
+		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
+		if ((rc = launch_scan(mt, mt->d_text, n, 0, ci * chunk_tiles, std::min(n_tiles, (ci + 1) * chunk_tiles),
+					 want_positions, mt->s_scan)))
+			return rc;
+		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
+	}
+	CU(cudaEventRecord(mt->ev_time[2 * n_chunks], mt->s_scan));
+	if (want_positions && n_tiles && (rc = finalize_positions(mt, n_tiles, 0, mt->s_scan)))
+		return rc;
+	CU(cudaEventRecord(mt->ev_time[2 * n_chunks + 1], mt->s_scan));
+	mt->last_want_positions = want_positions;
+	rc = acwm_fetch(mt, count, positions, cap, n_written, mt->s_scan);
+	double secs = 0;
+	for (uint64_t ci = 0; ci <= n_chunks; ci++) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, mt->ev_time[2 * ci], mt->ev_time[2 * ci + 1]) == cudaSuccess)
+			secs += ms * 1e-3;
+	}
+	mt->last_kernel_s = secs;
+	return rc;
+}
+
+double acwm_last_kernel_seconds(const acwm_matcher *mt) { return mt ? mt->last_kernel_s : 0.0; }
+
+unsigned long long acwm_launch_count(const acwm_matcher *mt) { return mt ? mt->launches : 0; }
+
+int acwm_get_info(const acwm_matcher *mt, acwm_info *info) {
+	if (!mt || !info)
+		return set_error(ACWM_ERR_INVALID, "NULL argument");
+	*info = mt->c.info;
+	return ACWM_OK;
+}
+
+void acwm_free(acwm_matcher *mt) {
+	if (!mt)
+		return;
+	if (mt->uploaded) {
+		cudaSetDevice(mt->device);
+		cudaFree(mt->d_front);
+		cudaFree(mt->d_filter2);
+		cudaFree(mt->d_bucket_start);
+		cudaFree(mt->d_entries);
+		cudaFree(mt->d_patterns);
+		cudaFree(mt->d_ctl);
+		cudaFree(mt->d_block_sums);
+		if (mt->d_staging)
+			cudaFree(mt->d_staging);
+		if (mt->d_positions)
+			cudaFree(mt->d_positions);
+		if (mt->d_tile_count)
+			cudaFree(mt->d_tile_count);
+		if (mt->d_text)
+			cudaFree(mt->d_text);
+		if (mt->h_ctl)
+			cudaFreeHost(mt->h_ctl);
+		if (mt->s_copy)
+			cudaStreamDestroy(mt->s_copy);
+		if (mt->s_scan)
+			cudaStreamDestroy(mt->s_scan);
+		for (auto e : mt->ev_copy)
+			if (e)
+				cudaEventDestroy(e);
+		for (auto e : mt->ev_time)
+			cudaEventDestroy(e);
+		(void) cudaGetLastError();
+	}
+	delete mt;
+}
+
+void acwm_shard_bounds(uint64_t n, uint32_t world, uint32_t rank, uint32_t halo, uint64_t *start, uint64_t *len) {
+	if (world == 0)
+		world = 1;
+	const uint64_t chunk = (n + world - 1) / world; // main.c:375: ceil(nFull / commSize)
+	uint64_t s = (uint64_t) rank * chunk, e = (uint64_t) (rank + 1) * chunk + halo; // main.c:469-471
+	if (e > n)
+		e = n; // main.c:472-473
+	if (s > n)
+		s = n;
+	if (start)
+		*start = s;
+	if (len)
+		*len = e > s ? e - s : 0;
+}
+
+int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_t *bytes) {
+	if (!mt || !ptr || !bytes)
+		return set_error(ACWM_ERR_INVALID, "NULL argument");
+	const Compiled &c = mt->c;
+	switch (which) {
+	case ACWM_BLOB_FRONT: *ptr = c.front.data(); *bytes = c.front.size(); break;
+	case ACWM_BLOB_FILTER2: *ptr = c.filter2.data(); *bytes = c.filter2.size() * 4; break;
+	case ACWM_BLOB_BUCKET_START: *ptr = c.bucket_start.data(); *bytes = c.bucket_start.size() * 4; break;
+	case ACWM_BLOB_ENTRIES: *ptr = c.entries.data(); *bytes = c.entries.size() * sizeof(acwm_ventry); break;
+	case ACWM_BLOB_PATTERNS: *ptr = mt->ps.bytes.data(); *bytes = mt->ps.bytes.size(); break;
+	case ACWM_BLOB_PARAMS: *ptr = &c.prm; *bytes = sizeof(c.prm); break;
+	case ACWM_BLOB_SYMCLASS: *ptr = c.symclass.data(); *bytes = c.symclass.size(); break;
+	default: return set_error(ACWM_ERR_INVALID, "unknown blob id");
+	}
+	return ACWM_OK;
+}
+
+} // extern "C"

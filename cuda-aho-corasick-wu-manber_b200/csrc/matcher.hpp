@@ -1,0 +1,49 @@
+// The matcher handle behind the C ABI (include/acwm.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <array>
+#include <string>
+#include <vector>
+
+#include "scan_common.cuh"
+#include "tables.hpp"
+
+namespace acwm {
+
+constexpr uint32_t kMaxScanBlocks = 4096;
+
+int set_error(int code, const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+
+} // namespace acwm
+
+struct acwm_matcher {
+	acwm::PatternSet ps;
+	acwm::Compiled c;
+	acwm_options opts{};
+	// device residency
+	bool uploaded = false;
+	int device = -1, sm_count = 0;
+	size_t l2_persist_max = 0, l2_window_max = 0;
+	uint8_t *d_front = nullptr;
+	uint32_t *d_filter2 = nullptr;
+	uint32_t *d_bucket_start = nullptr;
+	acwm_ventry *d_entries = nullptr;
+	uint8_t *d_patterns = nullptr;
+	acwm::Control *d_ctl = nullptr, *h_ctl = nullptr;
+	uint64_t *d_staging = nullptr, *d_positions = nullptr;
+	uint64_t pos_cap = 0;
+	uint32_t *d_tile_count = nullptr;
+	uint64_t tile_cap = 0;
+	unsigned long long *d_block_sums = nullptr;
+	// host-text pipeline
+	uint8_t *d_text = nullptr;
+	uint64_t text_cap = 0;
+	cudaStream_t s_copy = nullptr, s_scan = nullptr;
+	std::array<cudaEvent_t, 4> ev_copy{};
+	std::vector<cudaEvent_t> ev_time;
+	double last_kernel_s = 0;
+	int last_want_positions = 0;
+	unsigned long long launches = 0;
+};

@@ -1,0 +1,640 @@
+// Host-side table compiler (see tables.hpp).  Pure C++, no CUDA.
+#include "tables.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+#include "geometry.hpp"
+
+namespace acwm {
+
+// ------------------------------------------------------------------ pattern set
+static uint64_t fnv1a(const uint8_t *p, size_t n) {
+	uint64_t h = 1469598103934665603ull;
+	for (size_t i = 0; i < n; i++) {
+		h ^= p[i];
+		h *= 1099511628211ull;
+	}
+	return h;
+}
+
+int normalize_patterns(const uint8_t *patterns, const uint32_t *lens, uint32_t m, uint32_t p, uint32_t alphabet,
+		PatternSet &out, std::string &err) {
+	if (!patterns || p == 0) {
+		err = "empty pattern set";
+		return ACWM_ERR_INVALID;
+	}
+	if (alphabet < 2 || alphabet > 256) {
+		err = "alphabet must be in [2, 256] (symbols are unsigned char codes, ac/ac.c:136)";
+		return ACWM_ERR_INVALID;
+	}
+	if (!lens && m == 0) {
+		err = "pattern length m must be >= 1";
+		return ACWM_ERR_INVALID;
+	}
+	out = PatternSet();
+	out.alphabet = alphabet;
+	out.p_in = p;
+	std::unordered_multimap<uint64_t, uint32_t> seen;
+	seen.reserve((size_t) p * 2);
+	uint64_t at = 0;
+	for (uint32_t j = 0; j < p; j++) {
+		const uint32_t L = lens ? lens[j] : m;
+		if (L == 0) {
+			err = "zero-length pattern";
+			return ACWM_ERR_INVALID;
+		}
+		const uint8_t *s = patterns + at;
+		at += L;
+		for (uint32_t i = 0; i < L; i++)
+			if (s[i] >= alphabet) {
+				err = "pattern symbol >= alphabet";
+				return ACWM_ERR_INVALID;
+			}
+		const uint64_t h = fnv1a(s, L) ^ ((uint64_t) L << 48);
+		bool dup = false;
+		auto range = seen.equal_range(h);
+		for (auto it = range.first; it != range.second; ++it) {
+			const uint32_t k = it->second;
+			if (out.len[k] == L && memcmp(out.pat(k), s, L) == 0) {
+				dup = true;
+				break;
+			}
+		}
+		if (dup)
+			continue; // identical patterns collapse onto one terminal state (ac/ac.c:183)
+		seen.emplace(h, out.size());
+		out.off.push_back(out.bytes.size());
+		out.len.push_back(L);
+		out.bytes.insert(out.bytes.end(), s, s + L);
+	}
+	out.m_min = *std::min_element(out.len.begin(), out.len.end());
+	out.m_max = *std::max_element(out.len.begin(), out.len.end());
+	return ACWM_OK;
+}
+
+// ------------------------------------------------------------------ helpers
+static uint32_t ceil_log2(uint64_t v) {
+	uint32_t b = 0;
+	while (((uint64_t) 1 << b) < v)
+		b++;
+	return b;
+}
+
+static const uint32_t kMultF1 = 0x9E3779B1u;  // stage-1 block hash
+static const uint32_t kMultF2 = 0x85EBCA77u;  // stage-2 suffix hash
+static const uint32_t kMultHB = 0xC2B2AE3Du;  // bucket hash
+
+static inline void set_bit(std::vector<uint32_t> &bm, uint32_t idx) { bm[idx >> 5] |= 1u << (idx & 31); }
+
+// Key of a pattern for stage 2 / buckets: the last b2 symbols.
+static uint32_t pattern_key(const PatternSet &ps, uint32_t j, bool packed, uint32_t b2) {
+	if (packed)
+		return pack2_tail(ps.pat(j), ps.len[j], b2);
+	return mix64to32(pack8_tail(ps.pat(j), ps.len[j], b2));
+}
+
+// Stage 2 (suffix bitmap) + verification buckets, shared by WM and truncated AC.
+static void build_verify(const PatternSet &ps, bool packed, Compiled &c) {
+	acwm_scan_params &prm = c.prm;
+	const uint32_t pd = ps.size();
+	const uint32_t b2 = packed ? std::min<uint32_t>(ps.m_min, 16) : std::min<uint32_t>(ps.m_min, 8);
+	prm.b2 = b2;
+	// stage-2 bitmap: direct index when the key space is small, hashed otherwise
+	const uint32_t key_bits = packed ? 2 * b2 : 32;
+	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 64), 13), 19);
+	if (packed && key_bits <= f2bits) {
+		f2bits = std::max<uint32_t>(key_bits, 5);
+		prm.f2_mult = 1;
+		prm.f2_sh = 0;
+	} else {
+		prm.f2_mult = kMultF2;
+		prm.f2_sh = 32 - f2bits;
+	}
+	prm.f2_words = (1u << f2bits) / 32;
+	c.filter2.assign(prm.f2_words, 0);
+	// buckets
+	const uint32_t hbits = std::max<uint32_t>(ceil_log2((uint64_t) pd * 2), 4);
+	prm.hb_mult = kMultHB;
+	prm.hb_sh = 32 - hbits;
+	prm.n_buckets = 1u << hbits;
+	prm.n_entries = pd;
+	c.bucket_start.assign((size_t) prm.n_buckets + 1, 0);
+	std::vector<uint32_t> key(pd), bkt(pd);
+	for (uint32_t j = 0; j < pd; j++) {
+		key[j] = pattern_key(ps, j, packed, b2);
+		set_bit(c.filter2, (uint32_t) ((uint32_t) (key[j] * prm.f2_mult) >> prm.f2_sh));
+		bkt[j] = (uint32_t) (key[j] * prm.hb_mult) >> prm.hb_sh;
+		c.bucket_start[bkt[j] + 1]++;
+	}
+	for (uint32_t b = 0; b < prm.n_buckets; b++)
+		c.bucket_start[b + 1] += c.bucket_start[b];
+	c.entries.assign(pd, acwm_ventry{});
+	std::vector<uint32_t> fill(c.bucket_start.begin(), c.bucket_start.end() - 1);
+	for (uint32_t j = 0; j < pd; j++) {
+		acwm_ventry &e = c.entries[fill[bkt[j]]++];
+		e.key = key[j];
+		e.len = ps.len[j];
+		if (packed && ps.len[j] <= b2)
+			e.len |= 0x80000000u; // the key is the whole pattern
+		e.offset = ps.off[j];
+	}
+}
+
+// ------------------------------------------------------------------ AC: suffix trie -> DFA
+struct Trie {
+	uint32_t A = 0, D = 0;
+	std::vector<int32_t> go;     // [nodes * A]
+	std::vector<uint8_t> depth;
+	uint32_t rows = 0, leaves = 0;
+	bool overflow = false;
+	uint32_t nodes() const { return (uint32_t) depth.size(); }
+};
+
+// Trie of the last D symbols of every pattern (symbols mapped through cls[] when given).
+static void build_suffix_trie(const PatternSet &ps, uint32_t D, uint32_t A, const uint8_t *cls, uint32_t max_rows,
+		Trie &t) {
+	t = Trie();
+	t.A = A;
+	t.D = D;
+	t.go.assign(A, -1);
+	t.depth.assign(1, 0);
+	t.rows = 1;
+	for (uint32_t j = 0; j < ps.size(); j++) {
+		const uint8_t *s = ps.pat(j) + (ps.len[j] - D);
+		uint32_t st = 0;
+		for (uint32_t i = 0; i < D; i++) {
+			const uint32_t c = cls ? cls[s[i]] : s[i];
+			int32_t nx = t.go[(size_t) st * A + c];
+			if (nx < 0) {
+				nx = (int32_t) t.nodes();
+				t.go[(size_t) st * A + c] = nx;
+				t.go.insert(t.go.end(), A, -1);
+				t.depth.push_back((uint8_t) (i + 1));
+				if (i + 1 < D) {
+					if (++t.rows > max_rows) {
+						t.overflow = true;
+						return;
+					}
+				} else
+					t.leaves++;
+			}
+			st = (uint32_t) nx;
+		}
+	}
+}
+
+// One-step DFA over the rows (nodes of depth < D), failure function folded in.
+// next1[row*A + c] = (next_row << 1) | hit, where hit = the transition reached a
+// depth-D node (its successor row is that node's failure state, which behaves
+// identically from then on because a depth-D node has no children).
+static void build_dfa1(const Trie &t, std::vector<uint32_t> &next1, uint32_t &n_rows) {
+	const uint32_t A = t.A, D = t.D, N = t.nodes();
+	std::vector<int32_t> row(N, -1), fail(N, 0);
+	std::vector<uint32_t> order;
+	order.reserve(N);
+	std::vector<uint32_t> dnode((size_t) N * A, 0); // full delta over nodes (targets may be leaves)
+	order.push_back(0);
+	n_rows = 0;
+	for (size_t qi = 0; qi < order.size(); qi++) {
+		const uint32_t u = order[qi];
+		if (t.depth[u] >= D)
+			continue; // leaf: no row, no outgoing goto
+		row[u] = (int32_t) n_rows++;
+		for (uint32_t c = 0; c < A; c++) {
+			const int32_t v = t.go[(size_t) u * A + c];
+			if (v >= 0) {
+				fail[v] = (u == 0) ? 0 : (int32_t) dnode[(size_t) fail[u] * A + c];
+				dnode[(size_t) u * A + c] = (uint32_t) v;
+				order.push_back((uint32_t) v);
+			} else
+				dnode[(size_t) u * A + c] = (u == 0) ? 0 : dnode[(size_t) fail[u] * A + c];
+		}
+	}
+	next1.assign((size_t) n_rows * A, 0);
+	for (uint32_t u = 0; u < N; u++) {
+		if (row[u] < 0)
+			continue;
+		for (uint32_t c = 0; c < A; c++) {
+			uint32_t v = dnode[(size_t) u * A + c];
+			uint32_t hit = 0;
+			if (t.depth[v] >= D) {
+				hit = 1;
+				v = (uint32_t) fail[v];
+			}
+			next1[(size_t) row[u] * A + c] = ((uint32_t) row[v] << 1) | hit;
+		}
+	}
+}
+
+static uint32_t full_trie_states(const PatternSet &ps, uint32_t A_hint) {
+	// idcounter of the reference automaton (smatcher.h:50): nodes of the prefix trie.
+	(void) A_hint;
+	std::unordered_map<uint64_t, uint32_t> edge; // (state << 8 | sym) -> child
+	edge.reserve((size_t) ps.bytes.size() * 2);
+	uint32_t n = 1;
+	for (uint32_t j = 0; j < ps.size(); j++) {
+		uint32_t st = 0;
+		const uint8_t *s = ps.pat(j);
+		for (uint32_t i = 0; i < ps.len[j]; i++) {
+			auto it = edge.find(((uint64_t) st << 8) | s[i]);
+			if (it == edge.end()) {
+				edge.emplace(((uint64_t) st << 8) | s[i], n);
+				st = n++;
+			} else
+				st = it->second;
+		}
+	}
+	return n;
+}
+
+static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uint32_t budget, Compiled &c,
+		std::string &err) {
+	acwm_scan_params &prm = c.prm;
+	const uint32_t m = ps.m_min;
+	const uint32_t Dmax = std::min<uint32_t>(m, kHaloSyms);
+	// cost model (lane-instructions per symbol): 7 per DFA lookup, ~25 per verified candidate
+	double best_cost = 1e30;
+	uint32_t bestK = 0, bestD = 0;
+	uint32_t d_lo = 1, d_hi = Dmax;
+	if (opts.force_depth) {
+		d_lo = d_hi = std::min<uint32_t>(std::max<uint32_t>(opts.force_depth, 1), Dmax);
+	}
+	const uint32_t max_rows_any = std::min<uint32_t>(budget / 8, (1u << 15) - 1); // K = 1
+	for (uint32_t D = d_hi; D >= d_lo; D--) {
+		Trie t;
+		build_suffix_trie(ps, D, 4, nullptr, max_rows_any, t);
+		if (t.overflow)
+			continue;
+		const bool exact = (D == m);
+		const double rate = exact ? 0.0 : std::min(1.0, (double) t.leaves / std::pow(4.0, (double) D));
+		for (uint32_t K = 3; K >= 1; K--) {
+			if (opts.force_stride && opts.force_stride != K)
+				continue;
+			const uint64_t bytes = (uint64_t) t.rows << (2 * K + 1);
+			if (bytes > budget || t.rows >= (1u << (16 - K)))
+				continue;
+			const double cost = 7.0 / K + rate * 25.0;
+			if (cost < best_cost - 1e-9) {
+				best_cost = cost;
+				bestK = K;
+				bestD = D;
+			}
+		}
+	}
+	if (!bestK) {
+		err = "AC: no (stride, depth) fits the shared-memory table budget";
+		return ACWM_ERR_UNSUPPORTED;
+	}
+	Trie t;
+	build_suffix_trie(ps, bestD, 4, nullptr, max_rows_any, t);
+	std::vector<uint32_t> next1;
+	uint32_t n_rows = 0;
+	build_dfa1(t, next1, n_rows);
+	const uint32_t K = bestK, cols = 1u << (2 * K);
+	c.front_entry_bytes = 2;
+	c.front.assign((size_t) n_rows * cols * 2, 0);
+	uint16_t *tab = reinterpret_cast<uint16_t *>(c.front.data());
+	for (uint32_t r = 0; r < n_rows; r++)
+		for (uint32_t idx = 0; idx < cols; idx++) {
+			uint32_t st = r, hits = 0;
+			for (uint32_t i = 0; i < K; i++) {
+				const uint32_t e = next1[(size_t) st * 4 + ((idx >> (2 * i)) & 3)];
+				hits |= (e & 1) << i;
+				st = e >> 1;
+			}
+			tab[(size_t) r * cols + idx] = (uint16_t) ((st << K) | hits);
+		}
+	prm.stride = K;
+	prm.depth = bestD;
+	prm.exact_front = (bestD == m) ? 1 : 0;
+	prm.n_rows = n_rows;
+	if (!prm.exact_front)
+		build_verify(ps, true, c);
+	c.info.table_in_smem = 1;
+	return ACWM_OK;
+}
+
+static int compile_ac_bytes(const PatternSet &ps, const acwm_options &opts, uint32_t budget, Compiled &c,
+		std::string &err) {
+	acwm_scan_params &prm = c.prm;
+	const uint32_t m = ps.m_min;
+	// columns: symbol codes clamped to `alphabet` (one extra class for out-of-alphabet bytes)
+	uint32_t ncols = 1;
+	while (ncols < std::min<uint32_t>(ps.alphabet + 1, 256))
+		ncols <<= 1;
+	// class(b) = min(b, alphabet): every out-of-alphabet text byte shares the one class no
+	// pattern uses (the kernel computes the same min arithmetically; this copy is for tests)
+	c.symclass.resize(256);
+	for (uint32_t b = 0; b < 256; b++)
+		c.symclass[b] = (uint8_t) std::min<uint32_t>(b, std::min<uint32_t>(ps.alphabet, 255));
+	const uint32_t Dmax = std::min<uint32_t>(m, kHaloBytes);
+	double best_cost = 1e30;
+	uint32_t bestD = 0;
+	bool best_smem = true;
+	uint32_t d_lo = 1, d_hi = std::min<uint32_t>(Dmax, 8);
+	if (m <= kHaloBytes && m > d_hi)
+		d_hi = m; // also try the exact automaton
+	if (opts.force_depth)
+		d_lo = d_hi = std::min<uint32_t>(std::max<uint32_t>(opts.force_depth, 1), Dmax);
+	const uint32_t max_rows_global = 1u << 22;
+	for (uint32_t D = d_hi; D >= d_lo; D--) {
+		if (D > 8 && D != m && !opts.force_depth)
+			continue;
+		Trie t;
+		build_suffix_trie(ps, D, ncols, c.symclass.data(), max_rows_global, t);
+		if (t.overflow)
+			continue;
+		const bool exact = (D == m);
+		const double rate = exact ? 0.0 : std::min(1.0, (double) t.leaves / std::pow((double) ps.alphabet, (double) D));
+		const uint64_t smem_bytes = (uint64_t) t.rows * ncols * 2;
+		const bool fits = smem_bytes <= budget && t.rows < (1u << 15);
+		// one lookup per symbol: ~8 lane-instructions from shared memory, ~40 from L2
+		const double cost = (fits ? 8.0 : 40.0) + rate * 30.0;
+		if (cost < best_cost - 1e-9 && ((uint64_t) t.rows * ncols * 4 <= (1ull << 31))) {
+			best_cost = cost;
+			bestD = D;
+			best_smem = fits;
+		}
+	}
+	if (!bestD) {
+		err = "AC: automaton too large";
+		return ACWM_ERR_UNSUPPORTED;
+	}
+	Trie t;
+	build_suffix_trie(ps, bestD, ncols, c.symclass.data(), max_rows_global, t);
+	std::vector<uint32_t> next1;
+	uint32_t n_rows = 0;
+	build_dfa1(t, next1, n_rows);
+	if (best_smem) {
+		c.front_entry_bytes = 2;
+		c.front.assign((size_t) n_rows * ncols * 2, 0);
+		uint16_t *tab = reinterpret_cast<uint16_t *>(c.front.data());
+		for (size_t i = 0; i < (size_t) n_rows * ncols; i++)
+			tab[i] = (uint16_t) next1[i];
+	} else {
+		c.front_entry_bytes = 4;
+		c.front.assign((size_t) n_rows * ncols * 4, 0);
+		memcpy(c.front.data(), next1.data(), c.front.size());
+	}
+	prm.stride = 1;
+	prm.depth = bestD;
+	prm.exact_front = (bestD == m) ? 1 : 0;
+	prm.n_rows = n_rows;
+	prm.n_classes = ncols;
+	if (!prm.exact_front)
+		build_verify(ps, false, c);
+	c.info.table_in_smem = best_smem ? 1 : 0;
+	return ACWM_OK;
+}
+
+// ------------------------------------------------------------------ WM
+// Stage 1 = the SHIFT table of Wu-Manber evaluated at a fixed stride s instead of a
+// data-dependent skip: a sample position c is a candidate iff some pattern holds the
+// block text[c-B+1..c] at distance r < s from its end, i.e. iff SHIFT[block] < s
+// (wu/wu.c:126-128 computes the same minimum distance).  Every occurrence ending at
+// e is covered by the sample c = e - r, r = e mod-aligned distance < s, because
+// B <= m_min - s + 1 keeps the block inside the occurrence.
+static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packed, uint32_t budget, Compiled &c,
+		std::string &err) {
+	acwm_scan_params &prm = c.prm;
+	const uint32_t pd = ps.size();
+	const uint32_t Bcap = packed ? 16 : 8;
+	const double sigma_bits = packed ? 2.0 : std::log2((double) ps.alphabet);
+	const uint32_t max_fbits = std::min<uint32_t>(ceil_log2((uint64_t) budget * 8 + 1) - 1, 20);
+	double best_cost = 1e30;
+	uint32_t bestS = 0;
+	for (uint32_t s : {16u, 8u, 4u, 2u, 1u}) {
+		if (opts.force_stride && opts.force_stride != s)
+			continue;
+		if (s > ps.m_min)
+			continue;
+		const uint32_t B = std::min<uint32_t>(Bcap, ps.m_min - s + 1);
+		const double space_bits = std::min<double>(B * sigma_bits, (double) max_fbits);
+		const double load = (double) s * pd / std::pow(2.0, space_bits);
+		const double rate = 1.0 - std::exp(-load);
+		// per symbol: 11/s for the sampled filter + `rate` stage-2 probes of ~12
+		const double cost = (packed ? 11.0 : 13.0) / s + rate * 12.0;
+		if (cost < best_cost - 1e-9) {
+			best_cost = cost;
+			bestS = s;
+		}
+	}
+	if (!bestS) {
+		err = "WM: no sampling stride fits (pattern shorter than the forced stride?)";
+		return ACWM_ERR_INVALID;
+	}
+	const uint32_t s = bestS;
+	const uint32_t B = std::min<uint32_t>(Bcap, ps.m_min - s + 1);
+	prm.stride = s;
+	prm.depth = B;
+	prm.exact_front = 0;
+	uint32_t fbits;
+	if (packed && 2 * B <= max_fbits) {
+		fbits = std::max<uint32_t>(2 * B, 5);
+		prm.f1_mult = 1;
+		prm.f1_sh2 = 0;
+	} else {
+		fbits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 32), 13), max_fbits);
+		prm.f1_mult = kMultF1;
+		prm.f1_sh2 = 32 - fbits;
+	}
+	prm.f1_sh1 = packed ? 32 - 2 * B : 64 - 8 * B; // drop symbols older than the block
+	prm.f1_words = (1u << fbits) / 32;
+	std::vector<uint32_t> bm(prm.f1_words, 0);
+	for (uint32_t j = 0; j < pd; j++)
+		for (uint32_t r = 0; r < s; r++) {
+			uint32_t v;
+			if (packed)
+				v = pack2_tail(ps.pat(j), ps.len[j], B, r);
+			else
+				v = mix64to32(pack8_tail(ps.pat(j), ps.len[j], B, r));
+			set_bit(bm, (uint32_t) (v * prm.f1_mult) >> prm.f1_sh2);
+		}
+	c.front_entry_bytes = 4;
+	c.front.resize((size_t) prm.f1_words * 4);
+	memcpy(c.front.data(), bm.data(), c.front.size());
+	build_verify(ps, packed, c);
+	c.info.table_in_smem = 1;
+	return ACWM_OK;
+}
+
+// ------------------------------------------------------------------ entry point
+int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Compiled &out, std::string &err) {
+	out = Compiled();
+	acwm_scan_params &prm = out.prm;
+	const bool packed = ps.alphabet <= 4 && !opts.force_bytes_path;
+	prm.algo = (uint32_t) algo;
+	prm.packed2bit = packed ? 1 : 0;
+	prm.alphabet = ps.alphabet;
+	prm.m_min = ps.m_min;
+	prm.m_max = ps.m_max;
+	uint32_t budget = opts.smem_table_budget ? opts.smem_table_budget : kDefaultTableBudget;
+	const uint32_t hard_cap = kMaxSmem - kSmemReserve - (packed ? 8 * kWarpSmemPacked : 4 * kWarpSmemBytes);
+	budget = std::min(budget, hard_cap);
+	int rc;
+	if (algo == ACWM_ALGO_AC) {
+		if (ps.m_min != ps.m_max) {
+			err = "Aho-Corasick path takes equal-length patterns (preproc_ac has a single m, ac/ac.c:224); "
+				  "use ACWM_ALGO_WM for mixed lengths";
+			return ACWM_ERR_UNSUPPORTED;
+		}
+		// leave room for the stage-2 bitmap in case the automaton gets truncated
+		const uint32_t ac_budget = budget > 24 * 1024 ? budget - 16 * 1024 : budget;
+		rc = packed ? compile_ac_packed(ps, opts, ac_budget, out, err) : compile_ac_bytes(ps, opts, ac_budget, out, err);
+	} else if (algo == ACWM_ALGO_WM) {
+		const uint32_t wm_budget = std::min<uint32_t>(budget, 128 * 1024) * 3 / 4;
+		rc = compile_wm(ps, opts, packed, wm_budget, out, err);
+	} else {
+		err = "unknown algorithm id";
+		return ACWM_ERR_INVALID;
+	}
+	if (rc != ACWM_OK)
+		return rc;
+	const uint32_t smem_tables = (out.info.table_in_smem ? (uint32_t) out.front.size() : 0)
+			+ (uint32_t) out.filter2.size() * 4;
+	const uint32_t threads = packed ? threads_for_tables_packed(smem_tables) : threads_for_tables_bytes(smem_tables);
+	if (!threads) {
+		err = "scan tables exceed shared memory";
+		return ACWM_ERR_UNSUPPORTED;
+	}
+	acwm_info &inf = out.info;
+	inf.algo = (uint32_t) algo;
+	inf.alphabet = ps.alphabet;
+	inf.n_patterns = ps.p_in;
+	inf.n_distinct = ps.size();
+	inf.m_min = ps.m_min;
+	inf.m_max = ps.m_max;
+	inf.packed2bit = prm.packed2bit;
+	inf.stride = prm.stride;
+	inf.depth = prm.depth;
+	inf.exact_front = prm.exact_front;
+	inf.n_rows = prm.n_rows;
+	inf.n_states = (algo == ACWM_ALGO_AC) ? full_trie_states(ps, ps.alphabet) : 0;
+	inf.threads = threads;
+	inf.smem_bytes = smem_tables + (threads / 32) * (packed ? kWarpSmemPacked : kWarpSmemBytes) + kSmemReserve;
+	inf.table_bytes = out.front.size() + out.filter2.size() * 4 + out.bucket_start.size() * 4
+			+ out.entries.size() * sizeof(acwm_ventry) + ps.bytes.size();
+	return ACWM_OK;
+}
+
+// ------------------------------------------------------------------ reference-layout tables (shims)
+void fill_reference_ac_tables(const uint8_t *const *rows, int m, int p, int alphabet, int *state_transition,
+		unsigned *state_supply, unsigned *state_final, unsigned *n_states, unsigned *n_distinct) {
+	// Same observable content as preproc_ac (ac/ac.c:224-245): root row zeroed first
+	// (:61-62), goto edges recorded as they are created with ids in creation order
+	// (:159-162), terminal flags (:186), failure ids of depth >= 2 states (:114).
+	// Cells the reference never writes are left as the caller initialised them; the
+	// trie itself is kept privately so the caller's initial contents do not matter.
+	const size_t A = (size_t) alphabet;
+	for (int c = 0; c < alphabet; c++)
+		state_transition[c] = 0;
+	std::unordered_map<uint64_t, uint32_t> edge; // (state << 8 | sym) -> child
+	edge.reserve((size_t) m * (size_t) p * 2);
+	struct Edge {
+		uint32_t from, sym, to;
+	};
+	std::vector<Edge> edges;
+	std::vector<uint8_t> fin(1, 0);
+	unsigned ns = 1, nd = 0;
+	for (int j = 0; j < p; j++) {
+		uint32_t st = 0;
+		for (int i = 0; i < m; i++) {
+			const uint32_t sym = rows[j][i];
+			auto it = edge.find(((uint64_t) st << 8) | sym);
+			if (it == edge.end()) {
+				edge.emplace(((uint64_t) st << 8) | sym, ns);
+				edges.push_back(Edge{st, sym, ns});
+				state_transition[st * A + sym] = (int) ns;
+				fin.push_back(0);
+				st = ns++;
+			} else
+				st = it->second;
+		}
+		if (!fin[st]) {
+			fin[st] = 1;
+			state_final[st] = 1;
+			nd++;
+		}
+	}
+	// children of each state, ascending symbol (the reference's BFS visits i = 0..alphabet-1)
+	std::sort(edges.begin(), edges.end(), [](const Edge &a, const Edge &b) {
+		return a.from != b.from ? a.from < b.from : a.sym < b.sym;
+	});
+	std::vector<uint32_t> first(ns + 1, 0);
+	for (const Edge &e : edges)
+		first[e.from + 1]++;
+	for (unsigned s = 0; s < ns; s++)
+		first[s + 1] += first[s];
+	auto go = [&](uint32_t st, uint32_t sym) -> int64_t {
+		auto it = edge.find(((uint64_t) st << 8) | sym);
+		return it == edge.end() ? -1 : (int64_t) it->second;
+	};
+	std::vector<uint32_t> queue;
+	queue.reserve(ns);
+	std::vector<uint32_t> fail(ns, 0);
+	for (uint32_t k = first[0]; k < first[1]; k++)
+		queue.push_back(edges[k].to);
+	for (size_t qi = 0; qi < queue.size(); qi++) {
+		const uint32_t cur = queue[qi];
+		for (uint32_t k = first[cur]; k < first[cur + 1]; k++) {
+			const uint32_t c = edges[k].sym, s = edges[k].to;
+			queue.push_back(s);
+			uint32_t st = fail[cur];
+			int64_t nx;
+			while ((nx = go(st, c)) < 0 && st != 0)
+				st = fail[st];
+			const uint32_t f = nx < 0 ? 0u : (uint32_t) nx; // root self-loop on an absent symbol
+			fail[s] = f;
+			state_supply[s] = f;
+		}
+	}
+	if (n_states)
+		*n_states = ns;
+	if (n_distinct)
+		*n_distinct = nd;
+}
+
+unsigned reference_wu_shiftsize(int alphabet) {
+	switch (alphabet) { // wu/wu.c:18-47
+	case 2: return 22;
+	case 4: return 64;
+	case 8: return 148;
+	case 20: return 400;
+	case 128: return 2668;
+	case 256: return 5356;
+	case 512: return 10732;
+	case 1024: return 21484;
+	default: return 0;
+	}
+}
+
+void fill_reference_wu_tables(const uint8_t *const *rows, const uint8_t *flat, int m, int p, int B, int nbits,
+		int *SHIFT, int *PREFIX_value, int *PREFIX_index, int *PREFIX_size) {
+	// wu/wu.c:109-149 / 211-251; the caller pre-initialised SHIFT and PREFIX_size (main.c:444-449)
+	for (int j = 0; j < p; j++) {
+		const uint8_t *s = rows ? rows[j] : flat + (size_t) j * m;
+		for (int q = m; q >= B; --q) {
+			unsigned h = s[q - 3];
+			h <<= nbits;
+			h += s[q - 2];
+			h <<= nbits;
+			h += s[q - 1];
+			const int shiftlen = m - q;
+			if (shiftlen < SHIFT[h])
+				SHIFT[h] = shiftlen;
+			if (shiftlen == 0) {
+				unsigned ph = s[0];
+				ph <<= nbits;
+				ph += s[1];
+				PREFIX_value[(size_t) h * p + PREFIX_size[h]] = (int) ph;
+				PREFIX_index[(size_t) h * p + PREFIX_size[h]] = j;
+				PREFIX_size[h]++;
+			}
+		}
+	}
+}
+
+} // namespace acwm

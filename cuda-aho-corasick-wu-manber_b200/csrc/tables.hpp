@@ -1,0 +1,81 @@
+// Host-side table compiler: pattern set -> scan tables (no CUDA in this file).
+//
+// Replaces the table-building half of the reference's preprocessing
+// (/root/reference/ac/ac.c:224-245 preproc_ac, wu/wu.c:109-149 preproc_wu): the
+// reference fills flat goto/failure/final arrays and dense SHIFT/PREFIX arrays that
+// its kernels walk one symbol at a time; here the same pattern set is compiled into
+//   * AC : a dense DFA with the failure function folded in, K symbols per lookup
+//          on the 2-bit-compressed alphabet (alphabet <= 4) or one class-compressed
+//          symbol per lookup (bytes path), end-anchored and depth-truncated when the
+//          full automaton does not fit (hits are then verified);
+//   * WM : a SHIFT-derived block bitmap sampled every s symbols (stage 1), a suffix
+//          bitmap (HASH stage 2) and CSR verification buckets (PREFIX/compare).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/acwm.h"
+
+namespace acwm {
+
+struct PatternSet {
+	uint32_t alphabet = 0;
+	uint32_t p_in = 0;            // patterns handed in (with duplicates)
+	uint32_t m_min = 0, m_max = 0;
+	std::vector<uint8_t> bytes;   // distinct patterns back to back, first-occurrence order
+	std::vector<uint64_t> off;
+	std::vector<uint32_t> len;
+	uint32_t size() const { return (uint32_t) len.size(); }
+	const uint8_t *pat(uint32_t j) const { return bytes.data() + off[j]; }
+};
+
+struct Compiled {
+	acwm_scan_params prm{};
+	acwm_info info{};
+	std::vector<uint8_t> front;          // AC: uint16 (smem) or uint32 (global) DFA entries; WM: uint32 bitmap words
+	std::vector<uint32_t> filter2;       // stage-2 suffix bitmap
+	std::vector<uint32_t> bucket_start;  // n_buckets + 1
+	std::vector<acwm_ventry> entries;
+	std::vector<uint8_t> symclass;       // bytes-path AC: 256 entries
+	uint32_t front_entry_bytes = 2;
+};
+
+// Geometry shared by the builder's cost model and the kernels.
+constexpr uint32_t kSmemPerSM = 227 * 1024;
+constexpr uint32_t kDefaultTableBudget = 144 * 1024;
+
+int normalize_patterns(const uint8_t *patterns, const uint32_t *lens, uint32_t m, uint32_t p, uint32_t alphabet,
+		PatternSet &out, std::string &err);
+
+int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Compiled &out, std::string &err);
+
+// Packed-symbol helpers (2 bits per symbol, older symbol at lower bits).
+inline uint32_t pack2_tail(const uint8_t *pat, uint32_t len, uint32_t nsym, uint32_t skip_from_end = 0) {
+	uint32_t v = 0;
+	for (uint32_t i = 0; i < nsym; i++)
+		v |= (uint32_t) (pat[len - skip_from_end - nsym + i] & 3u) << (2 * i);
+	return v;
+}
+// Byte helpers (8 bits per symbol, older symbol at lower bytes), up to 8 symbols.
+inline uint64_t pack8_tail(const uint8_t *pat, uint32_t len, uint32_t nsym, uint32_t skip_from_end = 0) {
+	uint64_t v = 0;
+	for (uint32_t i = 0; i < nsym; i++)
+		v |= (uint64_t) pat[len - skip_from_end - nsym + i] << (8 * i);
+	return v;
+}
+// 64-bit block -> 32-bit mix used by the bytes-path stage-1 filter (device mirrors it).
+inline uint32_t mix64to32(uint64_t v) {
+	uint32_t lo = (uint32_t) v, hi = (uint32_t) (v >> 32);
+	return lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+}
+
+// Reference-layout flat tables for the shims (same content the reference leaves in
+// its caller's arrays: ac/ac.c:61-62,114,162,186 and wu/wu.c:109-149).
+void fill_reference_ac_tables(const uint8_t *const *rows, int m, int p, int alphabet, int *state_transition,
+		unsigned *state_supply, unsigned *state_final, unsigned *n_states, unsigned *n_distinct);
+unsigned reference_wu_shiftsize(int alphabet);
+void fill_reference_wu_tables(const uint8_t *const *rows, const uint8_t *flat, int m, int p, int B, int nbits,
+		int *SHIFT, int *PREFIX_value, int *PREFIX_index, int *PREFIX_size);
+
+} // namespace acwm

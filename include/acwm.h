@@ -1,0 +1,251 @@
+/* acwm.h -- C ABI of libacwm_b200.so: B200-native Aho-Corasick / Wu-Manber
+ * multi-pattern scan (count + every match position), the drop-in for the search
+ * path of iassael/cuda-aho-corasick-wu-manber.
+ *
+ * Plain C, `extern "C"`, pointers + sizes only.  Two layers:
+ *
+ *   1. NATIVE handle API (acwm_*): build tables once on the host, upload once,
+ *      scan host- or device-resident text of any size (64-bit), get the count and
+ *      the sorted match positions.  Status codes, never exit().
+ *
+ *   2. REFERENCE-SHAPED SHIMS with the exact names and parameter lists of the
+ *      reference's entry points, so the reference's main.c links against this
+ *      library unchanged:
+ *        preproc_ac / search_ac / free_ac            smatcher.h:89-91, ac/ac.c:198-252
+ *        preproc_wu / preproc_wu2                    smatcher.h:101-102, wu/wu.c:109,211
+ *        search_wu / search_wu2                      smatcher.h:105-106, wu/wu.c:49,151
+ *        wu_determine_shiftsize                      smatcher.h:103, wu/wu.c:18
+ *        cuda_ac1..cuda_ac5                          cuda/cuda_ac.cu:594,691,788,885,983
+ *        cuda_wm1..cuda_wm5                          cuda/cuda_wm.cu:183,438,652,854,1060
+ *      The shims run the scan on the GPU (there is no CPU search path in this
+ *      library); like the reference (cuda/cuda.h:26-47) they print and exit(1) on
+ *      a CUDA failure because their signatures have no error channel.
+ *
+ * Result definition (derived from ac/ac.c:207-219 and
+ * wu/wu.c:163-206): with Pset the DISTINCT patterns,
+ *     M = { (e, P) : P in Pset, len(P)-1 <= e < n, text[e-len(P)+1 .. e] == P }.
+ * count = |M|; positions = the e of every element of M, ascending; e is the 0-based
+ * index of the LAST byte of the occurrence (`column`, ac/ac.c:217, wu/wu.c:93).
+ * With equal-length patterns (the only case the reference supports) at most one
+ * pattern matches per e and count equals what search_ac / search_wu return.
+ *
+ * Text and pattern bytes are symbol codes in [0, alphabet), one byte per symbol,
+ * exactly as in the reference (ac/ac.c:136,209; wu/wu.c:63-67): DNA is bytes 0..3.
+ */
+#ifndef ACWM_H
+#define ACWM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACWM_VERSION 1
+
+/* ------------------------------ status codes ------------------------------ */
+enum {
+	ACWM_OK = 0,
+	ACWM_ERR_INVALID = 1,     /* bad argument (NULL, m < 1, symbol >= alphabet in a pattern, ...) */
+	ACWM_ERR_UNSUPPORTED = 2, /* valid request this build does not serve (e.g. mixed-length AC) */
+	ACWM_ERR_CUDA = 3,        /* CUDA runtime/driver failure; acwm_last_error() has the string */
+	ACWM_ERR_NOMEM = 4,       /* host or device allocation failed */
+	ACWM_ERR_OVERFLOW = 5,    /* more matches than the position capacity: count is exact, positions are not */
+	ACWM_ERR_BAD_TEXT = 6     /* a text byte >= 4 was met on the 2-bit (alphabet <= 4) path */
+};
+
+enum { ACWM_ALGO_AC = 0, ACWM_ALGO_WM = 1 };
+
+typedef struct acwm_matcher acwm_matcher; /* opaque: host tables + (after upload) device tables and buffers */
+
+/* Build-time options; zero-initialise for defaults. */
+typedef struct acwm_options {
+	uint32_t smem_table_budget; /* bytes of shared memory the scan tables may take per SM; 0 = default */
+	uint32_t force_stride;      /* AC: symbols per DFA lookup (1,2,3); WM: sampling stride (1,2,4,8,16); 0 = auto */
+	uint32_t force_depth;       /* AC: truncate the automaton at this depth (candidates are verified); 0 = auto */
+	uint32_t force_bytes_path;  /* 1 = use the byte-per-symbol kernels even when alphabet <= 4 */
+	uint32_t force_threads;     /* threads per CTA of the scan kernel (tuning); 0 = auto */
+	uint32_t reserved[3];
+} acwm_options;
+
+/* What the builder chose; for reports and tests. */
+typedef struct acwm_info {
+	uint32_t algo, alphabet, n_patterns, n_distinct, m_min, m_max;
+	uint32_t packed2bit;    /* 1: alphabet <= 4 path (text packed to 2 bits/symbol inside the kernel) */
+	uint32_t stride;        /* AC: symbols per lookup; WM: sampling stride s */
+	uint32_t depth;         /* AC: automaton depth D (== m_max: exact); WM: block length B (symbols) */
+	uint32_t exact_front;   /* 1: the front-end alone is exact (no verification stage) */
+	uint32_t n_states;      /* AC: trie states of the FULL automaton (idcounter, smatcher.h:50) */
+	uint32_t n_rows;        /* AC: rows of the device DFA */
+	uint32_t table_in_smem; /* 1: front-end table lives in shared memory, 0: global/L2 (access-policy window) */
+	uint32_t smem_bytes;    /* dynamic shared memory per CTA of the scan kernel */
+	uint64_t table_bytes;   /* bytes of device tables */
+	uint32_t threads, reserved;
+} acwm_info;
+
+/* ------------------------------ native API ------------------------------ */
+
+/* Compile the pattern set into scan tables (host only; no CUDA call).
+ *   patterns: all pattern bytes back to back; lens == NULL -> p patterns of m bytes
+ *   each (the reference's flat `pattern2` layout, main.c:455-461), else lens[j] bytes
+ *   for pattern j (mixed lengths: WM only).  Duplicates are allowed and collapse.
+ * Replaces preproc_ac (ac/ac.c:224) / preproc_wu (wu/wu.c:109). */
+int acwm_build(int algo, const uint8_t *patterns, const uint32_t *lens, uint32_t m, uint32_t p, uint32_t alphabet,
+		const acwm_options *opts, acwm_matcher **out);
+
+/* Upload the tables to `device` (-1 = current) and allocate the per-matcher
+ * device buffers.  Implicit on first search.  pos_capacity = how many match
+ * positions the device staging buffers can hold (0 = count-only matcher). */
+int acwm_upload(acwm_matcher *mt, int device, uint64_t pos_capacity);
+
+/* Scan DEVICE-resident text (resident in HBM; no host<->device copy of the text).
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ * Results stay on the device until acwm_fetch().  d_text needs no alignment.
+ * want_positions: 0 = count only, 1 = count + sorted positions.
+ * report_from: matches whose end index is < report_from are not reported (0 = report
+ * everything).  The sharding layer passes m_max-1 for every shard but the first so
+ * that, with mixed-length patterns too, each match is reported by exactly one shard;
+ * with equal-length patterns that is what a plain scan of the shard does anyway.
+ * Replaces the kernel launch inside cuda_ac5 / cuda_wm5 (cuda/cuda_ac.cu:654,
+ * cuda/cuda_wm.cu:276). */
+int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, int want_positions,
+		void *stream);
+
+/* Wait for the last scan on `stream` and fetch its results.  positions may be NULL
+ * (count only); at most cap positions are written; *n_written receives how many.
+ * Returns ACWM_ERR_OVERFLOW if count exceeded the capacity (count is still exact),
+ * ACWM_ERR_BAD_TEXT if the text held a byte >= 4 on the 2-bit path. */
+int acwm_fetch(acwm_matcher *mt, uint64_t *count, uint64_t *positions, uint64_t cap, uint64_t *n_written,
+		void *stream);
+
+/* Device pointers of the last scan's results, for callers that keep everything on
+ * the GPU (the multi-GPU layer all-reduces *d_count over NCCL): d_count points to
+ * one uint64 match count, d_positions to the sorted uint64 positions. */
+int acwm_result_device_ptrs(acwm_matcher *mt, uint64_t **d_count, uint64_t **d_positions);
+
+/* Scan HOST text end to end: chunked, pinned, double-buffered H2D overlapped with
+ * the scan, count + sorted positions back in host memory.  The call a reference
+ * user makes instead of cuda_ac5 / cuda_wm5; also what the search_* shims call. */
+int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t *count, uint64_t *positions,
+		uint64_t cap, uint64_t *n_written);
+
+/* Seconds of GPU time (CUDA events around the kernels only, as the reference times
+ * its kernels: cuda/cuda_wm.cu:264-289) of the last acwm_search_host call. */
+double acwm_last_kernel_seconds(const acwm_matcher *mt);
+
+/* Kernels this matcher has launched so far (scan + finalize), for bench reports. */
+unsigned long long acwm_launch_count(const acwm_matcher *mt);
+
+int acwm_get_info(const acwm_matcher *mt, acwm_info *info);
+void acwm_free(acwm_matcher *mt);
+
+/* Text of the last error on this thread ("" if none). */
+const char *acwm_last_error(void);
+
+/* Shard geometry of the multi-GPU layer == the MPI rank geometry of main.c:467-477:
+ * chunk = ceil(n/world); shard `rank` is text[start, start+len) with
+ * start = rank*chunk, len = min((rank+1)*chunk + halo, n) - start, halo = m_max-1.
+ * A plain scan of the shard reports local ends e_local in [m-1, len); the global
+ * end is start + e_local, so every match is found by exactly one shard. */
+void acwm_shard_bounds(uint64_t n, uint32_t world, uint32_t rank, uint32_t halo, uint64_t *start, uint64_t *len);
+
+/* Raw views of the compiled tables (tests and diagnostics).  `which` is one of the
+ * ACWM_BLOB_* ids; returns ACWM_ERR_INVALID if this matcher has no such table. */
+enum {
+	ACWM_BLOB_FRONT = 0,      /* AC: k-stride DFA (uint16 entries); WM: stage-1 block bitmap */
+	ACWM_BLOB_FILTER2 = 1,    /* stage-2 suffix bitmap */
+	ACWM_BLOB_BUCKET_START = 2,
+	ACWM_BLOB_ENTRIES = 3,    /* acwm_ventry[] */
+	ACWM_BLOB_PATTERNS = 4,   /* distinct pattern bytes, back to back */
+	ACWM_BLOB_PARAMS = 5,     /* acwm_scan_params */
+	ACWM_BLOB_SYMCLASS = 6    /* bytes path AC: 256-entry symbol -> class map */
+};
+int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_t *bytes);
+
+/* One pattern in the verification buckets. */
+typedef struct acwm_ventry {
+	uint32_t key;     /* packed last-B2 symbols of the pattern (what the text window must equal) */
+	uint32_t len;     /* pattern length; bit 31 set = key equality alone proves the match */
+	uint64_t offset;  /* byte offset of the pattern in the ACWM_BLOB_PATTERNS blob */
+} acwm_ventry;
+
+/* Scalar parameters the kernels run with (also what the test emulator reads). */
+typedef struct acwm_scan_params {
+	uint32_t algo, packed2bit, alphabet, m_min, m_max;
+	uint32_t stride;        /* K (AC) or s (WM) */
+	uint32_t depth;         /* D (AC) or B (WM) */
+	uint32_t exact_front;
+	uint32_t n_rows;        /* AC */
+	uint32_t f1_sh1, f1_mult, f1_sh2, f1_words;   /* WM stage 1: idx = ((v >> sh1) * mult) >> sh2 */
+	uint32_t b2;            /* stage-2 / bucket key length in symbols */
+	uint32_t f2_mult, f2_sh, f2_words;            /* idx2 = (key * mult) >> sh */
+	uint32_t hb_mult, hb_sh, n_buckets;           /* bucket = (key * mult) >> sh */
+	uint32_t n_entries;
+	uint32_t n_classes;     /* bytes path AC */
+	uint32_t reserved[8];
+} acwm_scan_params;
+
+/* ------------------- reference-shaped shims (smatcher.h) ------------------- */
+
+struct ac_state; /* smatcher.h:41-47; never dereferenced by callers of this path */
+struct ac_table { /* smatcher.h:49-53 -- same leading layout, so main.c compiles unchanged */
+	unsigned int idcounter;      /* number of states of the full automaton */
+	unsigned int patterncounter; /* number of distinct patterns */
+	struct ac_state *zerostate;  /* here: opaque pointer to the acwm_matcher */
+};
+
+/* Fills the caller's flat tables exactly as the reference does (state ids in
+ * creation order, -1 = no goto edge, root row 0: ac/ac.c:61-62,114,162,186) and
+ * compiles + uploads the device tables. */
+struct ac_table *preproc_ac(unsigned char **pattern, int m, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_supply, unsigned int *state_final);
+unsigned search_ac(unsigned char *text, int n, struct ac_table *table);
+void free_ac(struct ac_table *table, int alphabet);
+
+extern unsigned short m_nBitsInShift; /* smatcher.h:71 */
+extern unsigned int shiftsize;        /* smatcher.h:73 */
+void wu_determine_shiftsize(int alphabet);
+/* Fill SHIFT / PREFIX_* exactly as the reference does (wu/wu.c:109-149) and compile
+ * + upload the device tables (keyed by the SHIFT pointer for the search_* shims). */
+void preproc_wu(unsigned char **pattern, int m, int p_size, int alphabet, int B, int *SHIFT, int *PREFIX_value,
+		int *PREFIX_index, int *PREFIX_size);
+void preproc_wu2(unsigned char *pattern, int m, int p_size, int alphabet, int B, int *SHIFT, int *PREFIX_value,
+		int *PREFIX_index, int *PREFIX_size);
+unsigned int search_wu(unsigned char **pattern, int m, int p_size, unsigned char *text, int n, int *SHIFT,
+		int *PREFIX_value, int *PREFIX_index, int *PREFIX_size);
+unsigned int search_wu2(unsigned char *pattern, int m, int p_size, unsigned char *text, int n, int *SHIFT,
+		int *PREFIX_value, int *PREFIX_index, int *PREFIX_size);
+
+/* GPU wrappers.  The reference's cuda_acN print "Kernel N matches \t%i\t time \t%f"
+ * and return void (cuda/cuda_ac.cu:675); these print the same line.  The pattern
+ * set is recovered from the flat goto table (every terminal state spells one
+ * pattern).  cuda_wmN return the count and write the kernel seconds. */
+void cuda_ac1(int m, unsigned char *text, int n, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_supply, unsigned int *state_final);
+void cuda_ac2(int m, unsigned char *text, int n, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_supply, unsigned int *state_final);
+void cuda_ac3(int m, unsigned char *text, int n, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_supply, unsigned int *state_final);
+void cuda_ac4(int m, unsigned char *text, int n, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_supply, unsigned int *state_final);
+void cuda_ac5(int m, unsigned char *text, int n, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_supply, unsigned int *state_final);
+int cuda_wm1(unsigned char *pattern, int m, unsigned char *text, int n, int p_size, int alphabet, int B, int *SHIFT,
+		int *PREFIX_value, int *PREFIX_index, int *PREFIX_size, double *gpuTime);
+int cuda_wm2(unsigned char *pattern, int m, unsigned char *text, int n, int p_size, int alphabet, int B, int *SHIFT,
+		int *PREFIX_value, int *PREFIX_index, int *PREFIX_size, double *gpuTime);
+int cuda_wm3(unsigned char *pattern, int m, unsigned char *text, int n, int p_size, int alphabet, int B, int *SHIFT,
+		int *PREFIX_value, int *PREFIX_index, int *PREFIX_size, double *gpuTime);
+int cuda_wm4(unsigned char *pattern, int m, unsigned char *text, int n, int p_size, int alphabet, int B, int *SHIFT,
+		int *PREFIX_value, int *PREFIX_index, int *PREFIX_size, double *gpuTime);
+int cuda_wm5(unsigned char *pattern, int m, unsigned char *text, int n, int p_size, int alphabet, int B, int *SHIFT,
+		int *PREFIX_value, int *PREFIX_index, int *PREFIX_size, double *gpuTime);
+
+/* Count of the last cuda_acN call (the reference prints it and returns void). */
+unsigned long long acwm_shim_last_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACWM_H */

@@ -1,0 +1,176 @@
+"""TEST INFRASTRUCTURE ONLY: a numpy emulation of what the scan kernels do with the
+compiled tables (csrc/scan_packed.cu, csrc/scan_bytes.cu), used on the GPU-less CI box
+to check the table compiler (csrc/tables.cpp) and the chunk / warm-up / candidate logic
+against the oracle.  It reads the tables through ``acwm_table_blob`` and is never
+imported by the product.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import acwm_pkg
+
+acwm = acwm_pkg.load()
+
+M32 = np.uint64(0xFFFFFFFF)
+
+
+def _mul32(a, b):
+    return (a.astype(np.uint64) * np.uint64(b)) & M32
+
+
+def _mix64(v):
+    lo = v & M32
+    hi = v >> np.uint64(32)
+    return (lo * np.uint64(0x9E3779B1) + hi * np.uint64(0x85EBCA77)) & M32
+
+
+class Emulator:
+    def __init__(self, mt):
+        self.mt = mt
+        self.p = mt.params()
+        self.front = mt.blob(acwm.BLOB_FRONT)
+        self.f2 = mt.blob(acwm.BLOB_FILTER2).view(np.uint32)
+        self.bstart = mt.blob(acwm.BLOB_BUCKET_START).view(np.uint32)
+        self.entries = mt.blob(acwm.BLOB_ENTRIES).view(acwm.VENTRY_DTYPE)
+        self.pbytes = mt.blob(acwm.BLOB_PATTERNS)
+        self.info = mt.info
+
+    # ------------------------------------------------------------ windows
+    def _win16(self, sym):
+        """win[e] = 16 symbols ending at e, older symbol at lower bits (zeros before the text)."""
+        n = sym.size
+        pad = np.concatenate([np.zeros(15, np.uint64), sym.astype(np.uint64)])
+        w = np.zeros(n, np.uint64)
+        for i in range(16):
+            w |= pad[i:i + n] << np.uint64(2 * i)
+        return w
+
+    def _win8(self, text):
+        n = text.size
+        pad = np.concatenate([np.zeros(7, np.uint64), text.astype(np.uint64)])
+        w = np.zeros(n, np.uint64)
+        for i in range(8):
+            w |= pad[i:i + n] << np.uint64(8 * i)
+        return w
+
+    # ------------------------------------------------------------ verification
+    def _verify(self, text, ends, keys):
+        """ends/keys: candidate end positions and their stage-2 keys -> list of (e, mult)."""
+        p = self.p
+        n = text.size
+        i2 = _mul32(keys, p.f2_mult) >> np.uint64(p.f2_sh)
+        bits = (self.f2[(i2 >> np.uint64(5)).astype(np.int64)] >> (i2 & np.uint64(31)).astype(np.uint32)) & 1
+        out = []
+        for e, key in zip(ends[bits == 1].tolist(), keys[bits == 1].tolist()):
+            b = ((key * p.hb_mult) & 0xFFFFFFFF) >> p.hb_sh
+            mult = 0
+            for i in range(int(self.bstart[b]), int(self.bstart[b + 1])):
+                en = self.entries[i]
+                if int(en["key"]) != key:
+                    continue
+                ln = int(en["len"]) & 0x7FFFFFFF
+                if e + 1 < ln or e >= n:
+                    continue
+                if int(en["len"]) >> 31:
+                    mult += 1
+                else:
+                    off = int(en["offset"])
+                    mult += bool(np.array_equal(text[e + 1 - ln:e + 1], self.pbytes[off:off + ln]))
+            if mult:
+                out.append((e, mult))
+        return out
+
+    # ------------------------------------------------------------ front ends
+    def _ac_hits(self, sym, chunk, K_bits, cols_of):
+        """Generic chunked DFA walk; returns sorted hit positions (may include e >= n)."""
+        p = self.p
+        K = p.stride
+        D = p.depth
+        n = sym.size
+        nchunks = (n + chunk - 1) // chunk
+        wu = K * ((D - 1 + K - 1) // K)
+        ent_bytes = 2 if self.info["table_in_smem"] else 4
+        tab = self.front.view(np.uint16 if ent_bytes == 2 else np.uint32).astype(np.int64)
+        cols = cols_of
+        lo = -wu
+        total = nchunks * chunk
+        ext = np.zeros(total + wu, np.int64)
+        ext[wu:wu + n] = sym
+        starts = np.arange(nchunks, dtype=np.int64) * chunk
+        state = np.zeros(nchunks, np.int64)
+        hits = []
+        for t in range(lo // K, chunk // K):
+            idx = np.zeros(nchunks, np.int64)
+            for i in range(K):
+                idx |= ext[starts + wu + K * t + i] << (K_bits * i)
+            ent = tab[state * cols + idx]
+            state = ent >> K
+            h = ent & ((1 << K) - 1)
+            if t >= 0 and h.any():
+                for i in range(K):
+                    sel = np.nonzero((h >> i) & 1)[0]
+                    if sel.size:
+                        hits.append(starts[sel] + K * t + i)
+        if not hits:
+            return np.zeros(0, np.int64)
+        return np.sort(np.concatenate(hits))
+
+    def search(self, text):
+        """-> (count, positions) exactly as the kernels would produce them."""
+        p = self.p
+        text = np.ascontiguousarray(text, np.uint8)
+        n = text.size
+        if n == 0:
+            return 0, np.zeros(0, np.uint64)
+        m_min = p.m_min
+        if p.packed2bit:
+            assert int(text.max()) < 4, "bad text for the 2-bit path"
+            sym = text.astype(np.int64)
+            win = self._win16(text)
+            if p.algo == acwm.AC:
+                hits = self._ac_hits(sym, 192, 2, 1 << (2 * p.stride))
+                hits = hits[(hits >= m_min - 1) & (hits < n)]
+                if p.exact_front:
+                    return int(hits.size), hits.astype(np.uint64)
+                ends = hits
+            else:
+                s = p.stride
+                cpos = np.arange(0, ((n + 191) // 192) * 192, s, dtype=np.int64)
+                cin = cpos[cpos < n]
+                v = np.zeros(cpos.size, np.uint64)
+                v[:cin.size] = win[cin]
+                idx = _mul32(v >> np.uint64(p.f1_sh1), p.f1_mult) >> np.uint64(p.f1_sh2)
+                bm = self.front.view(np.uint32)
+                bit = (bm[(idx >> np.uint64(5)).astype(np.int64)] >> (idx & np.uint64(31)).astype(np.uint32)) & 1
+                cand = cpos[bit == 1]
+                ends = (cand[:, None] + np.arange(s)[None, :]).reshape(-1)
+                ends = ends[ends < n]
+            keys = win[ends] >> np.uint64(32 - 2 * p.b2)
+        else:
+            win = self._win8(text)
+            if p.algo == acwm.AC:
+                alpha = min(p.alphabet, 255)
+                cls = np.minimum(text.astype(np.int64), alpha)
+                lognc = int(p.n_classes).bit_length() - 1
+                hits = self._ac_hits(cls, 112, lognc, 1 << lognc)
+                hits = hits[(hits >= m_min - 1) & (hits < n)]
+                if p.exact_front:
+                    return int(hits.size), hits.astype(np.uint64)
+                ends = hits
+            else:
+                s = p.stride
+                cpos = np.arange(0, n, s, dtype=np.int64)
+                blk = win[cpos] >> np.uint64(p.f1_sh1)
+                idx = _mul32(_mix64(blk), p.f1_mult) >> np.uint64(p.f1_sh2)
+                bm = self.front.view(np.uint32)
+                bit = (bm[(idx >> np.uint64(5)).astype(np.int64)] >> (idx & np.uint64(31)).astype(np.uint32)) & 1
+                cand = cpos[bit == 1]
+                ends = (cand[:, None] + np.arange(s)[None, :]).reshape(-1)
+                ends = ends[ends < n]
+            keys = _mix64(win[ends] >> np.uint64(64 - 8 * p.b2))
+        res = self._verify(text, ends, keys)
+        pos = []
+        for e, mult in res:
+            pos.extend([e] * mult)
+        return len(pos), np.array(pos, np.uint64)
