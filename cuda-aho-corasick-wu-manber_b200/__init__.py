@@ -84,6 +84,8 @@ def lib():
         L.acwm_search_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p, C.c_void_p, C.c_uint64, _u64p]
         L.acwm_last_kernel_seconds.restype = C.c_double
         L.acwm_last_kernel_seconds.argtypes = [C.c_void_p]
+        L.acwm_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.acwm_profiled_seconds.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.acwm_launch_count.restype = C.c_ulonglong
         L.acwm_launch_count.argtypes = [C.c_void_p]
         L.acwm_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
@@ -215,6 +217,15 @@ class Matcher:
                     allow=(ERR_OVERFLOW,) if allow_overflow else ())
         self.last_rc = rc
         return int(count.value), pos[:int(nw.value)]
+
+    def set_profiling(self, on: bool):
+        _check(lib().acwm_set_profiling(self._h, int(on)))
+
+    def profiled_seconds(self):
+        """(scan kernel seconds, finalize kernels seconds) of the last profiled scan_device."""
+        a, b = C.c_double(), C.c_double()
+        _check(lib().acwm_profiled_seconds(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     @property
     def last_kernel_seconds(self) -> float:

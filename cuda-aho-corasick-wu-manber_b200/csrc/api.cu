@@ -257,10 +257,20 @@ int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64
 		return rc;
 	CU(cudaMemsetAsync(mt->d_ctl, 0, sizeof(Control), st));
 	apply_l2_window(mt, st);
+	if (mt->profiling) {
+		if (!mt->ev_prof[0])
+			for (auto &e : mt->ev_prof)
+				CU(cudaEventCreate(&e));
+		CU(cudaEventRecord(mt->ev_prof[0], st));
+	}
 	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, st)))
 		return rc;
+	if (mt->profiling)
+		CU(cudaEventRecord(mt->ev_prof[1], st));
 	if (want_positions && n_tiles && (rc = finalize_positions(mt, n_tiles, mis, st)))
 		return rc;
+	if (mt->profiling)
+		CU(cudaEventRecord(mt->ev_prof[2], st));
 	mt->last_want_positions = want_positions;
 	return ACWM_OK;
 }
@@ -366,6 +376,27 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 
 double acwm_last_kernel_seconds(const acwm_matcher *mt) { return mt ? mt->last_kernel_s : 0.0; }
 
+int acwm_set_profiling(acwm_matcher *mt, int on) {
+	if (!mt)
+		return set_error(ACWM_ERR_INVALID, "matcher == NULL");
+	mt->profiling = on != 0;
+	return ACWM_OK;
+}
+
+int acwm_profiled_seconds(acwm_matcher *mt, double *scan_s, double *finalize_s) {
+	if (!mt || !mt->profiling || !mt->ev_prof[0])
+		return set_error(ACWM_ERR_INVALID, "profiling is off or no scan was profiled");
+	CU(cudaEventSynchronize(mt->ev_prof[2]));
+	float a = 0, b = 0;
+	CU(cudaEventElapsedTime(&a, mt->ev_prof[0], mt->ev_prof[1]));
+	CU(cudaEventElapsedTime(&b, mt->ev_prof[1], mt->ev_prof[2]));
+	if (scan_s)
+		*scan_s = a * 1e-3;
+	if (finalize_s)
+		*finalize_s = b * 1e-3;
+	return ACWM_OK;
+}
+
 unsigned long long acwm_launch_count(const acwm_matcher *mt) { return mt ? mt->launches : 0; }
 
 int acwm_get_info(const acwm_matcher *mt, acwm_info *info) {
@@ -406,6 +437,9 @@ void acwm_free(acwm_matcher *mt) {
 				cudaEventDestroy(e);
 		for (auto e : mt->ev_time)
 			cudaEventDestroy(e);
+		for (auto e : mt->ev_prof)
+			if (e)
+				cudaEventDestroy(e);
 		(void) cudaGetLastError();
 	}
 	delete mt;

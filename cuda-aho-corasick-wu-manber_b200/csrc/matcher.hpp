@@ -43,6 +43,8 @@ struct acwm_matcher {
 	cudaStream_t s_copy = nullptr, s_scan = nullptr;
 	std::array<cudaEvent_t, 4> ev_copy{};
 	std::vector<cudaEvent_t> ev_time;
+	std::array<cudaEvent_t, 3> ev_prof{};
+	bool profiling = false;
 	double last_kernel_s = 0;
 	int last_want_positions = 0;
 	unsigned long long launches = 0;

@@ -134,6 +134,12 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
  * its kernels: cuda/cuda_wm.cu:264-289) of the last acwm_search_host call. */
 double acwm_last_kernel_seconds(const acwm_matcher *mt);
 
+/* Bench instrumentation: with profiling on, acwm_scan_device brackets the scan kernel and
+ * the finalize kernels with CUDA events on the caller's stream; acwm_profiled_seconds
+ * waits for the last profiled scan and returns the two durations. */
+int acwm_set_profiling(acwm_matcher *mt, int on);
+int acwm_profiled_seconds(acwm_matcher *mt, double *scan_s, double *finalize_s);
+
 /* Kernels this matcher has launched so far (scan + finalize), for bench reports. */
 unsigned long long acwm_launch_count(const acwm_matcher *mt);
 

@@ -1,0 +1,251 @@
+"""GPU parity tests proper: every call goes through the C ABI of libacwm_b200.so
+(acwm_search_host / acwm_scan_device + acwm_fetch / the reference-shaped shims) and is
+compared bit-exactly -- match count and every match position -- with the oracle on the
+same seeded inputs, with the committed golden vectors (reference counts), and at
+BASELINE sizes through size-independent properties as well."""
+import numpy as np
+import pytest
+
+from cases import RANDOM_CASES, edge_cases, make_case
+from golden_util import load_golden
+
+pytestmark = pytest.mark.gpu
+GOLD = load_golden()
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _check(acwm, oracle, algo, pats, alphabet, text, **opts):
+    mt = acwm.Matcher(algo, pats, alphabet, **opts)
+    count, pos = mt.search_host(text, cap=max(1, text.size * 2))
+    ref = oracle.set_search(pats, text)
+    assert count == ref["count"], (count, ref["count"], mt.info)
+    assert np.array_equal(pos, ref["positions"]), mt.info
+    return mt
+
+
+@pytest.mark.parametrize("case", RANDOM_CASES, ids=lambda c: c[0])
+def test_random_cases_match_oracle(acwm, oracle, torch_cuda, case):
+    name, algo, alphabet, p, m, n, opts = case
+    pats, text = make_case(case)
+    _check(acwm, oracle, algo, pats, alphabet, text, **opts).close()
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+@pytest.mark.parametrize("algo_name", ["AC", "WM"])
+def test_golden_vectors(acwm, torch_cuda, name, algo_name):
+    g = GOLD[name]
+    pats, text, alphabet = g["patterns"], g["text"], int(g["alphabet"])
+    algo = acwm.AC if algo_name == "AC" else acwm.WM
+    mt = acwm.Matcher(algo, pats, alphabet)
+    count, pos = mt.search_host(text, cap=max(1, text.size))
+    assert count == int(g["ref_ac_count"]) == int(g["ref_wu_count"])
+    assert np.array_equal(pos, g["positions"])
+    mt.close()
+
+
+def test_edge_cases(acwm, torch_cuda):
+    for name, alphabet, pats, text, exp in edge_cases():
+        for algo in (acwm.AC, acwm.WM):
+            for opts in ({}, dict(force_bytes_path=1)):
+                mt = acwm.Matcher(algo, pats, alphabet, **opts)
+                count, pos = mt.search_host(text, cap=64)
+                assert pos.tolist() == exp and count == len(exp), (name, algo, opts)
+                mt.close()
+
+
+def test_empty_text(acwm, torch_cuda):
+    mt = acwm.Matcher(acwm.AC, np.zeros((1, 4), np.uint8), 4)
+    count, pos = mt.search_host(np.zeros(0, np.uint8), cap=4)
+    assert count == 0 and pos.size == 0
+
+
+@pytest.mark.parametrize("threads", [256, 512, 768, 1024])
+def test_thread_variants_packed(acwm, oracle, torch_cuda, threads):
+    for cname in ("c1_ac_dna_p100_m8", "c2_wm_dna_p1000_m16", "ac_dna_depth5"):
+        case = next(c for c in RANDOM_CASES if c[0] == cname)
+        name, algo, alphabet, p, m, n, opts = case
+        pats, text = make_case(case)
+        _check(acwm, oracle, algo, pats, alphabet, text, force_threads=threads, **opts).close()
+
+
+@pytest.mark.parametrize("threads", [128, 256, 384, 512])
+def test_thread_variants_bytes(acwm, oracle, torch_cuda, threads):
+    for cname in ("wm_ascii_p1000_m8", "ac_protein_p100_m6"):
+        case = next(c for c in RANDOM_CASES if c[0] == cname)
+        name, algo, alphabet, p, m, n, opts = case
+        pats, text = make_case(case)
+        _check(acwm, oracle, algo, pats, alphabet, text, force_threads=threads, **opts).close()
+
+
+def test_device_resident_unaligned_and_report_from(acwm, oracle, torch_cuda):
+    torch = torch_cuda
+    for cname in ("c1_ac_dna_p100_m8", "c2_wm_dna_p1000_m16", "wm_ascii_p1000_m8", "ac_protein_p100_m6"):
+        case = next(c for c in RANDOM_CASES if c[0] == cname)
+        name, algo, alphabet, p, m, n, opts = case
+        pats, text = make_case(case)
+        mt = acwm.Matcher(algo, pats, alphabet, **opts).upload(pos_capacity=text.size)
+        d_all = torch.from_numpy(text).cuda()
+        st = torch.cuda.current_stream().cuda_stream
+        for off, ln in ((0, text.size), (1, 70_001), (5, 6144 * 3), (13, 50_000), (16, 3584 * 5 + 3), (31, 777)):
+            sub = d_all[off:off + ln]
+            mt.scan_tensor(sub)
+            count, pos, _ = mt.fetch(cap=text.size, stream=st)
+            ref = oracle.set_search(pats, text[off:off + ln])
+            assert count == ref["count"], (cname, off, ln)
+            assert np.array_equal(pos, ref["positions"]), (cname, off, ln)
+        # report_from drops exactly the ends below it
+        mt.scan_tensor(d_all, report_from=12345)
+        count, pos, _ = mt.fetch(cap=text.size, stream=st)
+        ref = oracle.set_search(pats, text)
+        keep = ref["positions"][ref["positions"] >= 12345]
+        assert count == keep.size and np.array_equal(pos, keep)
+        # count-only scan
+        mt.scan_tensor(d_all, want_positions=False)
+        count, pos, _ = mt.fetch(cap=0, stream=st)
+        assert count == ref["count"]
+        mt.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_scans_sum_to_whole(acwm, oracle, torch_cuda, world):
+    """The multi-GPU geometry run on one GPU: shard scans are exactly-once."""
+    torch = torch_cuda
+    sh = __import__("acwm_pkg").submodule("sharding")
+    for cname in ("c2_wm_dna_p1000_m16", "c4_wm_ascii_mixed_8_64", "ac_dna_p1000_m16_trunc"):
+        case = next(c for c in RANDOM_CASES if c[0] == cname)
+        name, algo, alphabet, p, m, n, opts = case
+        pats, text = make_case(case)
+        m_max = max(q.size for q in pats) if isinstance(pats, list) else pats.shape[1]
+        mt = acwm.Matcher(algo, pats, alphabet, **opts).upload(pos_capacity=text.size)
+        d_all = torch.from_numpy(text).cuda()
+        st = torch.cuda.current_stream().cuda_stream
+        got = []
+        for r in range(world):
+            start, length, report_from = sh.shard_of(text.size, world, r, m_max)
+            mt.scan_tensor(d_all[start:start + length], report_from=report_from)
+            count, pos, _ = mt.fetch(cap=text.size, stream=st)
+            assert count == pos.size
+            got.append(pos + np.uint64(start))
+        got = np.concatenate(got)
+        ref = oracle.set_search(pats, text)
+        assert got.size == ref["count"] and np.array_equal(got, ref["positions"])
+        mt.close()
+
+
+def test_overflow_and_bad_text(acwm, torch_cuda):
+    text = np.zeros(10_000, np.uint8)
+    mt = acwm.Matcher(acwm.AC, np.zeros((1, 4), np.uint8), 4)
+    count, pos = mt.search_host(text, cap=100, allow_overflow=True)
+    assert count == 10_000 - 3 and mt.last_rc == acwm.ERR_OVERFLOW
+    bad = text.copy()
+    bad[5000] = 9
+    with pytest.raises(acwm.AcwmError) as e:
+        mt.search_host(bad, cap=20_000)
+    assert e.value.code == acwm.ERR_BAD_TEXT
+    # after an error the matcher still works
+    count, pos = mt.search_host(text, cap=20_000)
+    assert count == 10_000 - 3 and np.array_equal(pos, np.arange(3, 10_000, dtype=np.uint64))
+    # the bytes path has no such restriction: out-of-alphabet bytes simply never match
+    mt2 = acwm.Matcher(acwm.AC, np.zeros((1, 4), np.uint8), 4, force_bytes_path=1)
+    count, pos = mt2.search_host(bad, cap=20_000)
+    assert count == 10_000 - 3 - 4
+
+
+def test_reference_shaped_shims(acwm, oracle, torch_cuda, capfd):
+    """Reads like the reference's own driver (main.c:125-157, 268-298, 582-648)."""
+    sm = __import__("acwm_pkg").submodule("smatcher")
+    case = RANDOM_CASES[0]
+    name, algo, alphabet, p, m, n, opts = case
+    pattern, text = make_case(case)
+    n = text.size
+    want = oracle.set_search(pattern, text)["count"]
+    # multiac
+    state_transition, state_supply, state_final = sm.alloc_ac_tables(m, p, alphabet)
+    table = sm.preproc_ac(pattern, m, p, alphabet, state_transition, state_supply, state_final)
+    assert sm.search_ac(text, n, table) == want
+    sm.free_ac(table, alphabet)
+    # cuda_ac1..5 work from the flat tables alone
+    for k in (1, 5):
+        assert sm.cuda_ac(k, m, text, n, p, alphabet, state_transition, state_supply, state_final) == want
+    out = capfd.readouterr().out
+    assert f"Kernel 5 matches \t{want}\t time" in out
+    # multiwm / multiwm2 + cuda_wm
+    case = RANDOM_CASES[1]
+    name, algo, alphabet, p, m, n, opts = case
+    pattern, text = make_case(case)
+    n = text.size
+    pattern2 = np.ascontiguousarray(pattern).reshape(-1)
+    want = oracle.set_search(pattern, text)["count"]
+    SHIFT, PV, PI, PS = sm.alloc_wu_tables(m, p, alphabet)
+    sm.preproc_wu(pattern, m, p, alphabet, 3, SHIFT, PV, PI, PS)
+    assert sm.search_wu(pattern, m, p, text, n, SHIFT, PV, PI, PS) == want
+    SHIFT2, PV2, PI2, PS2 = sm.alloc_wu_tables(m, p, alphabet)
+    sm.preproc_wu2(pattern2, m, p, alphabet, 3, SHIFT2, PV2, PI2, PS2)
+    assert sm.search_wu2(pattern2, m, p, text, n, SHIFT2, PV2, PI2, PS2) == want
+    cnt, secs = sm.cuda_wm(5, pattern2, m, text, n, p, alphabet, 3, SHIFT2, PV2, PI2, PS2)
+    assert cnt == want and secs > 0
+
+
+def test_baseline_configs_full_size(acwm, oracle, have_ref, torch_cuda):
+    """BASELINE configs 1 and 2 at their real size (128 MiB DNA): bit-exact against the
+    linear-time oracle, against the unmodified reference's count on a prefix, and through
+    size-independent properties (sorted, distinct, AC == WM on the same set, shard sums)."""
+    torch = torch_cuda
+    dg = __import__("acwm_pkg").submodule("datagen")
+    n = 128 << 20
+    text = dg.text_host(n, 4, 1)
+    d_text = torch.from_numpy(text).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    for algo, p, m in ((acwm.AC, 100, 8), (acwm.WM, 1000, 16)):
+        pats = dg.patterns_with_hits(text, p, m, 4, 2)
+        ref = oracle.set_search(pats, text)
+        mt = acwm.Matcher(algo, pats, 4).upload(pos_capacity=1 << 22)
+        mt.scan_tensor(d_text)
+        count, pos, _ = mt.fetch(cap=1 << 22, stream=st)
+        assert count == ref["count"]
+        assert np.array_equal(pos, ref["positions"])
+        assert np.all(pos[1:] > pos[:-1])
+        other = acwm.Matcher(acwm.WM if algo == acwm.AC else acwm.AC, pats, 4).upload(pos_capacity=1 << 22)
+        other.scan_tensor(d_text)
+        c2, p2, _ = other.fetch(cap=1 << 22, stream=st)
+        assert c2 == count and np.array_equal(p2, pos)
+        if have_ref:
+            pre = 8 << 20
+            rc = (oracle.ref_ac if algo == acwm.AC else oracle.ref_wu)(pats, 4, text[:pre])["count"]
+            assert rc == int(np.count_nonzero(pos < pre))
+        # host path, end to end
+        c3, p3 = mt.search_host(text, cap=1 << 22)
+        assert c3 == count and np.array_equal(p3, pos)
+        mt.close()
+        other.close()
+
+
+def test_multi_gib_text_positions_beyond_32_bits(acwm, torch_cuda):
+    """5 GiB DNA text resident in HBM: 64-bit positions, AC == WM, planted matches found."""
+    torch = torch_cuda
+    dg = __import__("acwm_pkg").submodule("datagen")
+    n = 5 << 30
+    d_text = dg.text_device(n, 4, 9)
+    rng = np.random.default_rng(3)
+    pats = rng.integers(0, 4, (64, 24), dtype=np.uint8)
+    plant = [23, 6143, 6144, (1 << 32) - 1, (1 << 32) + 5, n - 1]
+    for k, e in enumerate(plant):
+        d_text[e - 23:e + 1] = torch.from_numpy(pats[k]).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    res = []
+    for algo in (acwm.AC, acwm.WM):
+        mt = acwm.Matcher(algo, pats, 4).upload(pos_capacity=1 << 20)
+        mt.scan_tensor(d_text)
+        count, pos, _ = mt.fetch(cap=1 << 20, stream=st)
+        assert count == pos.size
+        assert set(plant) <= set(pos.tolist())
+        res.append(pos)
+        mt.close()
+    assert np.array_equal(res[0], res[1])
