@@ -235,7 +235,9 @@ def test_multi_gib_text_positions_beyond_32_bits(acwm, torch_cuda):
     d_text = dg.text_device(n, 4, 9)
     rng = np.random.default_rng(3)
     pats = rng.integers(0, 4, (64, 24), dtype=np.uint8)
-    plant = [23, 6143, 6144, (1 << 32) - 1, (1 << 32) + 5, n - 1]
+    # ends on both sides of a warp-tile edge and of the 2^32 boundary; >= 24 apart so the planted
+    # windows do not overwrite each other
+    plant = [23, 6143, 6144 + 30, 2 * 6144, (1 << 32) - 1, (1 << 32) + 29, n - 1]
     for k, e in enumerate(plant):
         d_text[e - 23:e + 1] = torch.from_numpy(pats[k]).cuda()
     st = torch.cuda.current_stream().cuda_stream
