@@ -37,14 +37,15 @@ class AcwmError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("smem_table_budget", C.c_uint32), ("force_stride", C.c_uint32), ("force_depth", C.c_uint32),
-                ("force_bytes_path", C.c_uint32), ("force_threads", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("force_bytes_path", C.c_uint32), ("force_threads", C.c_uint32), ("force_stages", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
 
 
 class Info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in
                 ("algo", "alphabet", "n_patterns", "n_distinct", "m_min", "m_max", "packed2bit", "stride", "depth",
                  "exact_front", "n_states", "n_rows", "table_in_smem", "smem_bytes")] + \
-               [("table_bytes", C.c_uint64), ("threads", C.c_uint32), ("reserved", C.c_uint32)]
+               [("table_bytes", C.c_uint64), ("threads", C.c_uint32), ("stages", C.c_uint32)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}

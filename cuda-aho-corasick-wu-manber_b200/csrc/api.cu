@@ -15,9 +15,6 @@ namespace acwm {
 
 cudaError_t launch_scan_packed(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st);
 cudaError_t launch_scan_bytes(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st);
-cudaError_t launch_finalize(uint32_t *tile_count, uint64_t n_tiles, unsigned long long *block_sums,
-		uint32_t max_blocks, const uint64_t *staging, uint64_t cap, uint32_t tile_syms, uint64_t data_lo,
-		uint64_t *positions, Control *ctl, int sm_count, cudaStream_t st);
 
 static thread_local std::string g_last_error;
 
@@ -101,8 +98,8 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 		return rc;
 	CU(cudaMalloc((void **) &mt->d_ctl, sizeof(Control)));
 	CU(cudaMemset(mt->d_ctl, 0, sizeof(Control)));
-	CU(cudaMallocHost((void **) &mt->h_ctl, sizeof(Control)));
-	CU(cudaMalloc((void **) &mt->d_block_sums, kMaxScanBlocks * sizeof(unsigned long long)));
+	CU(cudaMallocHost((void **) &mt->h_res, sizeof(Result)));
+	CU(cudaMalloc((void **) &mt->d_cta_total, kMaxScanBlocks * sizeof(unsigned long long)));
 	CU(cudaStreamCreateWithFlags(&mt->s_copy, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&mt->s_scan, cudaStreamNonBlocking));
 	for (auto &e : mt->ev_copy)
@@ -133,9 +130,10 @@ static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
 	(void) cudaGetLastError();
 }
 
-// Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes).
+// Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
+// cooperative kernel that scans, orders the positions and publishes the result block.
 static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
-		uint64_t tile_hi, int want_positions, cudaStream_t st) {
+		uint64_t tile_hi, int want_positions, int append, cudaStream_t st) {
 	const Compiled &c = mt->c;
 	ScanArgs a;
 	memset(&a, 0, sizeof(a));
@@ -156,30 +154,25 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.prm = c.prm;
 	a.ctl = mt->d_ctl;
 	a.staging = mt->d_staging;
+	a.positions = mt->d_positions;
 	a.cap = want_positions ? mt->pos_cap : 0;
 	a.tile_count = mt->d_tile_count;
+	a.cta_total = mt->d_cta_total;
+	a.stages = c.info.stages;
 	a.want_positions = want_positions;
+	a.append = append;
 	const uint32_t threads = c.info.threads, warps = threads / 32;
 	const uint64_t ntl = tile_hi - tile_lo;
-	const uint32_t grid = (uint32_t) std::min<uint64_t>((uint64_t) mt->sm_count, (ntl + warps - 1) / warps);
-	if (grid == 0)
-		return ACWM_OK;
+	// every CTA owns a contiguous span of whole "rounds" (one tile per warp)
+	uint32_t grid = (uint32_t) std::min<uint64_t>((uint64_t) mt->sm_count, (ntl + warps - 1) / warps);
+	grid = std::max(grid, 1u);
+	a.tiles_per_cta = std::max<uint64_t>(1, (ntl + grid - 1) / grid);
+	grid = (uint32_t) std::max<uint64_t>(1, (ntl + a.tiles_per_cta - 1) / a.tiles_per_cta);
 	cudaError_t e = c.prm.packed2bit ? launch_scan_packed(a, threads, c.info.smem_bytes, grid, st)
 									 : launch_scan_bytes(a, threads, c.info.smem_bytes, grid, st);
 	if (e != cudaSuccess)
 		return cuda_fail(e, "scan kernel launch");
 	mt->launches++;
-	return ACWM_OK;
-}
-
-static uint32_t tile_syms(const acwm_matcher *mt) { return mt->c.prm.packed2bit ? kWarpTile : kWarpTileB; }
-
-static int finalize_positions(acwm_matcher *mt, uint64_t n_tiles, uint64_t data_lo, cudaStream_t st) {
-	cudaError_t e = launch_finalize(mt->d_tile_count, n_tiles, mt->d_block_sums, kMaxScanBlocks, mt->d_staging,
-			mt->pos_cap, tile_syms(mt), data_lo, mt->d_positions, mt->d_ctl, mt->sm_count, st);
-	if (e != cudaSuccess)
-		return cuda_fail(e, "finalize launch");
-	mt->launches += 2;
 	return ACWM_OK;
 }
 
@@ -205,21 +198,6 @@ int acwm_build(int algo, const uint8_t *patterns, const uint32_t *lens, uint32_t
 	int rc = normalize_patterns(patterns, lens, m, p, alphabet, mt->ps, err);
 	if (rc == ACWM_OK)
 		rc = compile_tables(algo, mt->ps, mt->opts, mt->c, err);
-	if (rc == ACWM_OK && mt->opts.force_threads) { // force_threads (tuning / tests)
-		const uint32_t t = mt->opts.force_threads;
-		const bool packed = mt->c.prm.packed2bit;
-		const uint32_t per_warp = packed ? kWarpSmemPacked : kWarpSmemBytes;
-		const uint32_t tables = mt->c.info.smem_bytes - (mt->c.info.threads / 32) * per_warp;
-		const bool ok = packed ? (t == 1024 || t == 768 || t == 512 || t == 256)
-							   : (t == 512 || t == 384 || t == 256 || t == 128);
-		if (!ok || tables + (t / 32) * per_warp > kMaxSmem) {
-			err = "forced thread count not available for this table size";
-			rc = ACWM_ERR_INVALID;
-		} else {
-			mt->c.info.threads = t;
-			mt->c.info.smem_bytes = tables + (t / 32) * per_warp;
-		}
-	}
 	if (rc != ACWM_OK) {
 		delete mt;
 		return set_error(rc, err);
@@ -251,11 +229,10 @@ int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64
 		return set_error(ACWM_ERR_INVALID, "positions requested but the matcher was uploaded with pos_capacity = 0");
 	cudaStream_t st = (cudaStream_t) stream;
 	const uint64_t mis = (uint64_t) (uintptr_t) d_text & 15u;
-	const uint64_t T = tile_syms(mt);
-	const uint64_t n_tiles = n ? (mis + n + T - 1) / T : 0;
+	const uint64_t T = kTile;
+	const uint64_t n_tiles = (mis + n + T - 1) / T; // n == 0: no tile, the launch only publishes an empty result
 	if (want_positions && (rc = ensure_tiles(mt, n_tiles)))
 		return rc;
-	CU(cudaMemsetAsync(mt->d_ctl, 0, sizeof(Control), st));
 	apply_l2_window(mt, st);
 	if (mt->profiling) {
 		if (!mt->ev_prof[0])
@@ -263,14 +240,10 @@ int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64
 				CU(cudaEventCreate(&e));
 		CU(cudaEventRecord(mt->ev_prof[0], st));
 	}
-	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, st)))
+	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, 0, st)))
 		return rc;
 	if (mt->profiling)
 		CU(cudaEventRecord(mt->ev_prof[1], st));
-	if (want_positions && n_tiles && (rc = finalize_positions(mt, n_tiles, mis, st)))
-		return rc;
-	if (mt->profiling)
-		CU(cudaEventRecord(mt->ev_prof[2], st));
 	mt->last_want_positions = want_positions;
 	return ACWM_OK;
 }
@@ -280,9 +253,9 @@ int acwm_fetch(acwm_matcher *mt, uint64_t *count, uint64_t *positions, uint64_t 
 	if (!mt || !mt->uploaded)
 		return set_error(ACWM_ERR_INVALID, "matcher not uploaded");
 	cudaStream_t st = (cudaStream_t) stream;
-	CU(cudaMemcpyAsync(mt->h_ctl, mt->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(mt->h_res, &mt->d_ctl->result, sizeof(Result), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
-	const Control &h = *mt->h_ctl;
+	const Result &h = *mt->h_res;
 	if (count)
 		*count = h.count;
 	if (n_written)
@@ -296,7 +269,7 @@ int acwm_fetch(acwm_matcher *mt, uint64_t *count, uint64_t *positions, uint64_t 
 			CU(cudaMemcpy(positions, mt->d_positions, w * 8, cudaMemcpyDeviceToHost));
 		if (n_written)
 			*n_written = w;
-		if (h.cursor > mt->pos_cap || h.count > cap)
+		if (h.overflow || h.count > cap)
 			return set_error(ACWM_ERR_OVERFLOW, "more matches than position capacity");
 	}
 	return ACWM_OK;
@@ -306,7 +279,7 @@ int acwm_result_device_ptrs(acwm_matcher *mt, uint64_t **d_count, uint64_t **d_p
 	if (!mt || !mt->uploaded)
 		return set_error(ACWM_ERR_INVALID, "matcher not uploaded");
 	if (d_count)
-		*d_count = reinterpret_cast<uint64_t *>(&mt->d_ctl->count);
+		*d_count = reinterpret_cast<uint64_t *>(&mt->d_ctl->result.count);
 	if (d_positions)
 		*d_positions = mt->d_positions;
 	return ACWM_OK;
@@ -331,41 +304,38 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		CU(cudaMalloc((void **) &mt->d_text, n + 64));
 		mt->text_cap = n + 64;
 	}
-	const uint64_t T = tile_syms(mt);
-	const uint64_t n_tiles = n ? (n + T - 1) / T : 0;
+	const uint64_t T = kTile;
+	const uint64_t n_tiles = (n + T - 1) / T;
 	if (want_positions && (rc = ensure_tiles(mt, n_tiles)))
 		return rc;
 	// chunks of ~32 MiB, whole tiles each: H2D on s_copy, scan on s_scan as soon as the chunk
-	// (and, through stream order, everything before it -- the halo) has landed
+	// (and, through stream order, everything before it -- the halo) has landed; every launch
+	// after the first appends its count and its (sorted) positions to the result block
 	const uint64_t chunk_tiles = std::max<uint64_t>(1, (32ull << 20) / T);
-	const uint64_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
-	while (mt->ev_time.size() < 2 * n_chunks + 2) {
+	const uint64_t n_chunks = std::max<uint64_t>(1, (n_tiles + chunk_tiles - 1) / chunk_tiles);
+	while (mt->ev_time.size() < 2 * n_chunks) {
 		cudaEvent_t e;
 		CU(cudaEventCreate(&e));
 		mt->ev_time.push_back(e);
 	}
-	CU(cudaMemsetAsync(mt->d_ctl, 0, sizeof(Control), mt->s_scan));
 	apply_l2_window(mt, mt->s_scan);
 	for (uint64_t ci = 0; ci < n_chunks; ci++) {
-		const uint64_t b0 = ci * chunk_tiles * T, b1 = std::min<uint64_t>(n, (ci + 1) * chunk_tiles * T);
-		CU(cudaMemcpyAsync(mt->d_text + b0, text + b0, b1 - b0, cudaMemcpyHostToDevice, mt->s_copy));
+		const uint64_t b0 = std::min<uint64_t>(n, ci * chunk_tiles * T), b1 = std::min<uint64_t>(n, (ci + 1) * chunk_tiles * T);
+		if (b1 > b0)
+			CU(cudaMemcpyAsync(mt->d_text + b0, text + b0, b1 - b0, cudaMemcpyHostToDevice, mt->s_copy));
 		cudaEvent_t ev = mt->ev_copy[ci % mt->ev_copy.size()];
 		CU(cudaEventRecord(ev, mt->s_copy));
 		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
 		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
-		if ((rc = launch_scan(mt, mt->d_text, n, 0, ci * chunk_tiles, std::min(n_tiles, (ci + 1) * chunk_tiles),
-					 want_positions, mt->s_scan)))
+		if ((rc = launch_scan(mt, mt->d_text, n, 0, std::min(n_tiles, ci * chunk_tiles),
+					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, mt->s_scan)))
 			return rc;
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
 	}
-	CU(cudaEventRecord(mt->ev_time[2 * n_chunks], mt->s_scan));
-	if (want_positions && n_tiles && (rc = finalize_positions(mt, n_tiles, 0, mt->s_scan)))
-		return rc;
-	CU(cudaEventRecord(mt->ev_time[2 * n_chunks + 1], mt->s_scan));
 	mt->last_want_positions = want_positions;
 	rc = acwm_fetch(mt, count, positions, cap, n_written, mt->s_scan);
 	double secs = 0;
-	for (uint64_t ci = 0; ci <= n_chunks; ci++) {
+	for (uint64_t ci = 0; ci < n_chunks; ci++) {
 		float ms = 0;
 		if (cudaEventElapsedTime(&ms, mt->ev_time[2 * ci], mt->ev_time[2 * ci + 1]) == cudaSuccess)
 			secs += ms * 1e-3;
@@ -386,10 +356,9 @@ int acwm_set_profiling(acwm_matcher *mt, int on) {
 int acwm_profiled_seconds(acwm_matcher *mt, double *scan_s, double *finalize_s) {
 	if (!mt || !mt->profiling || !mt->ev_prof[0])
 		return set_error(ACWM_ERR_INVALID, "profiling is off or no scan was profiled");
-	CU(cudaEventSynchronize(mt->ev_prof[2]));
-	float a = 0, b = 0;
+	CU(cudaEventSynchronize(mt->ev_prof[1]));
+	float a = 0, b = 0; // the ordering of the positions is fused into the scan kernel: no separate finalize time
 	CU(cudaEventElapsedTime(&a, mt->ev_prof[0], mt->ev_prof[1]));
-	CU(cudaEventElapsedTime(&b, mt->ev_prof[1], mt->ev_prof[2]));
 	if (scan_s)
 		*scan_s = a * 1e-3;
 	if (finalize_s)
@@ -417,7 +386,7 @@ void acwm_free(acwm_matcher *mt) {
 		cudaFree(mt->d_entries);
 		cudaFree(mt->d_patterns);
 		cudaFree(mt->d_ctl);
-		cudaFree(mt->d_block_sums);
+		cudaFree(mt->d_cta_total);
 		if (mt->d_staging)
 			cudaFree(mt->d_staging);
 		if (mt->d_positions)
@@ -426,8 +395,8 @@ void acwm_free(acwm_matcher *mt) {
 			cudaFree(mt->d_tile_count);
 		if (mt->d_text)
 			cudaFree(mt->d_text);
-		if (mt->h_ctl)
-			cudaFreeHost(mt->h_ctl);
+		if (mt->h_res)
+			cudaFreeHost(mt->h_res);
 		if (mt->s_copy)
 			cudaStreamDestroy(mt->s_copy);
 		if (mt->s_scan)

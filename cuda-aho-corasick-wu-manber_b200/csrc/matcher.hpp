@@ -31,19 +31,20 @@ struct acwm_matcher {
 	uint32_t *d_bucket_start = nullptr;
 	acwm_ventry *d_entries = nullptr;
 	uint8_t *d_patterns = nullptr;
-	acwm::Control *d_ctl = nullptr, *h_ctl = nullptr;
+	acwm::Control *d_ctl = nullptr;
+	acwm::Result *h_res = nullptr;
 	uint64_t *d_staging = nullptr, *d_positions = nullptr;
 	uint64_t pos_cap = 0;
 	uint32_t *d_tile_count = nullptr;
 	uint64_t tile_cap = 0;
-	unsigned long long *d_block_sums = nullptr;
+	unsigned long long *d_cta_total = nullptr;
 	// host-text pipeline
 	uint8_t *d_text = nullptr;
 	uint64_t text_cap = 0;
 	cudaStream_t s_copy = nullptr, s_scan = nullptr;
 	std::array<cudaEvent_t, 4> ev_copy{};
 	std::vector<cudaEvent_t> ev_time;
-	std::array<cudaEvent_t, 3> ev_prof{};
+	std::array<cudaEvent_t, 2> ev_prof{};
 	bool profiling = false;
 	double last_kernel_s = 0;
 	int last_want_positions = 0;

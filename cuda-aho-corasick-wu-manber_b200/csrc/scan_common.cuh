@@ -1,4 +1,4 @@
-// Device-side pieces shared by the 2-bit and the bytes scan kernels (sm_100a).
+// Device-side pieces shared by the 2-bit and the bytes front ends (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -8,13 +8,28 @@
 
 namespace acwm {
 
-// Device control block of one matcher (zeroed before every scan).
-struct Control {
-	unsigned long long count;    // |M|
-	unsigned long long cursor;   // staging slots handed out
-	unsigned long long written;  // positions written by the finalize pass
+// What a finished scan leaves behind for acwm_fetch / the multi-GPU layer.
+struct Result {
+	unsigned long long count;    // |M| (cumulative over the launches of one search)
+	unsigned long long written;  // positions placed in the output (cumulative)
 	unsigned int bad_text;       // OR of (byte & 0xFC) over the text, 2-bit path
-	unsigned int overflow;       // staging capacity exceeded
+	unsigned int overflow;       // more matches than position capacity
+};
+
+// Working counters of the launch in flight.  All zero between launches: the last CTA
+// of every launch folds them into `result` and clears them, so no memset is needed.
+struct Work {
+	unsigned long long count;
+	unsigned long long cursor;   // staging slots handed out
+	unsigned int bad_text;
+	unsigned int arrived;        // grid barrier
+	unsigned int done;           // exit ticket
+	unsigned int pad;
+};
+
+struct Control {
+	Result result;
+	Work work;
 };
 
 struct ScanArgs {
@@ -22,6 +37,7 @@ struct ScanArgs {
 	uint64_t data_lo, data_hi;   // real text occupies virtual [data_lo, data_hi), data_lo < 16
 	uint64_t report_lo;          // matches ending before this virtual position are not reported
 	uint64_t tile_lo, tile_hi;   // warp tiles [tile_lo, tile_hi) of the virtual text are scanned by this launch
+	uint64_t tiles_per_cta;      // CTA b owns tiles [tile_lo + b*tiles_per_cta, +tiles_per_cta) (clipped to tile_hi)
 	const uint8_t *front;        // front-end table (global copy)
 	uint32_t front_bytes;
 	uint32_t front_in_smem;
@@ -31,10 +47,14 @@ struct ScanArgs {
 	const uint8_t *patterns;
 	acwm_scan_params prm;
 	Control *ctl;
-	uint64_t *staging;           // [tile:28 | rank:22 | pos:13]
-	uint64_t cap;
-	uint32_t *tile_count;        // matches per tile (when want_positions)
+	uint64_t *staging;           // [tile:28 | rank:22 | pos:14]
+	uint64_t *positions;         // sorted output
+	uint64_t cap;                // capacity of staging and of positions (entries)
+	uint32_t *tile_count;        // matches per tile -> (in the epilogue) exclusive prefix within the owning CTA
+	unsigned long long *cta_total; // matches per CTA
+	uint32_t stages;             // ring depth of the per-warp tile pipeline
 	int want_positions;
+	int append;                  // 1: add to ctl->result instead of replacing it (chunked host text)
 };
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -62,9 +82,67 @@ __device__ __forceinline__ uint64_t encode_stage(uint64_t tile, uint32_t rank, u
 	return (tile << (kRankBits + kPosBits)) | ((uint64_t) rank << kPosBits) | pos;
 }
 
+// ------------------------------------------------------------ mbarrier / TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+			"{\n"
+			".reg .pred p;\n"
+			"WAIT_%=:\n"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+			"@p bra DONE_%=;\n"
+			"bra WAIT_%=;\n"
+			"DONE_%=:\n"
+			"}\n" ::"r"(smem_u32(bar)),
+			"r"(parity)
+			: "memory");
+}
+// L2 policy for the text stream: read once, evict first (keeps L2-resident tables in place)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+	asm volatile(
+			"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+					smem_u32(dst)),
+			"l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+			: "memory");
+}
+
+// ------------------------------------------------------------ grid barrier (cooperative launch: all CTAs resident)
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+	unsigned int v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned int *arrived) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		atomicAdd(arrived, 1u);
+		while (ld_acquire_u32(arrived) < gridDim.x)
+			__nanosleep(64);
+		__threadfence();
+	}
+	__syncthreads();
+}
+
 // Warp-collective emission of matches found at `pos` (tile-relative) with
 // multiplicity `mult` (0 = none) per lane, lanes in ascending position order.
-// Returns the number emitted; advances tile_rank.
 struct Emitter {
 	const ScanArgs *a;
 	uint64_t tile;
@@ -87,7 +165,7 @@ struct Emitter {
 		if (a->want_positions) {
 			unsigned long long slot0 = 0;
 			if (lane_id() == 0)
-				slot0 = atomicAdd(&a->ctl->cursor, (unsigned long long) total);
+				slot0 = atomicAdd(&a->ctl->work.cursor, (unsigned long long) total);
 			slot0 = __shfl_sync(kFull, slot0, 0);
 			for (uint32_t i = 0; i < mult; i++) {
 				const unsigned long long slot = slot0 + excl + i;

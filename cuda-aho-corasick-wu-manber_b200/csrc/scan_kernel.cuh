@@ -1,0 +1,379 @@
+// The scan kernel skeleton (sm_100a), shared by every front end.
+//
+// ONE cooperative launch does the whole job -- supersedes the reference's
+// kernel + D2H of 7680 per-thread counters + host sum (cuda/cuda_ac.cu:654-673):
+//
+//   1. scan     one persistent CTA per SM owns a contiguous span of warp tiles; every warp
+//               runs its own TMA pipeline over the span (cp.async.bulk global -> shared,
+//               mbarrier complete_tx, 2-3 tiles in flight per warp, no block-wide barrier),
+//               walks its front end over the raw tile and stages each match as
+//               [tile | rank-in-tile | pos-in-tile] through one warp-aggregated atomic;
+//   2. order    the CTA turns the per-tile counts of its span into exclusive offsets, all
+//               CTAs meet at one grid barrier, every CTA derives the span bases from the
+//               per-CTA totals and the staged matches drop into their sorted slots;
+//   3. publish  the last CTA out folds the working counters into the result block and
+//               clears them for the next launch (no memset node between scans).
+#pragma once
+#include "scan_common.cuh"
+
+namespace acwm {
+
+// Careful loader for the first / last tiles of the text: never touches a byte outside
+// [data_lo, data_hi); everything else in the buffer becomes zero.
+static __device__ __noinline__ void load_tile_edge(const ScanArgs &a, uint64_t tile, uint8_t *buf) {
+	const long long base = (long long) (tile * (uint64_t) kTile) - (long long) kHalo;
+	for (int c = (int) lane_id(); c < (int) (kLoadBytes / 16); c += 32) {
+		const long long off = base + 16ll * c;
+		uint4 r = make_uint4(0, 0, 0, 0);
+		if (off >= (long long) a.data_lo && off + 16 <= (long long) a.data_hi)
+			r = ldg_stream16(a.text16 + off);
+		else if (off + 16 > (long long) a.data_lo && off < (long long) a.data_hi) {
+			uint32_t w[4] = {0, 0, 0, 0};
+			for (int k = 0; k < 16; k++) {
+				const long long pos = off + k;
+				if (pos >= (long long) a.data_lo && pos < (long long) a.data_hi)
+					w[k >> 2] |= (uint32_t) a.text16[pos] << (8 * (k & 3));
+			}
+			r = make_uint4(w[0], w[1], w[2], w[3]);
+		}
+		*reinterpret_cast<uint4 *>(buf + 16 * c) = r;
+	}
+}
+
+__device__ __forceinline__ bool tile_is_interior(const ScanArgs &a, uint64_t tile) {
+	return tile >= 1 && (tile + 1) * (uint64_t) kTile <= (a.data_hi & ~(uint64_t) 15);
+}
+
+template <class Front, bool EXACT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant__ ScanArgs a) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	constexpr uint32_t W = THREADS / 32;
+	// [CTA scratch 1 KiB][front table][stage-2 bitmap][per-warp areas]
+	uint64_t *tab_bar = reinterpret_cast<uint64_t *>(smem);
+	uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + 64); // 33 words
+	const uint32_t front_smem = a.front_in_smem ? ((a.front_bytes + 15u) & ~15u) : 0u;
+	const uint32_t f2_bytes = EXACT ? 0u : ((a.prm.f2_words * 4u + 15u) & ~15u);
+	uint8_t *s_front = smem + kSmemReserve;
+	uint32_t *s_f2 = reinterpret_cast<uint32_t *>(s_front + front_smem);
+	uint8_t *s_warps = s_front + front_smem + f2_bytes;
+
+	const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+	const uint32_t stages = a.stages;
+	uint8_t *wbase = s_warps + warp * warp_smem_bytes(stages);
+	uint8_t *bufs = wbase;
+	uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + stages * kBufBytes);
+	uint16_t *queue = reinterpret_cast<uint16_t *>(pk + kPackWords);
+	uint64_t *bars = reinterpret_cast<uint64_t *>(queue + kQueueCap);
+
+	if (threadIdx.x == 0)
+		mbar_init(tab_bar, 1);
+	if (lane == 0)
+		for (uint32_t s = 0; s < stages; s++)
+			mbar_init(&bars[s], 1);
+	if (lane < 4)
+		for (uint32_t s = 0; s < stages; s++) // pad behind each buffer: read, never used
+			reinterpret_cast<uint32_t *>(bufs + s * kBufBytes + kLoadBytes)[lane] = 0;
+	if (lane < 3)
+		pk[kPackWords - 3 + lane] = 0;
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	__syncthreads();
+
+	// tables: global -> shared with TMA bulk copies, overlapped with the first text tiles
+	const uint32_t tab_bytes = front_smem + f2_bytes;
+	if (threadIdx.x == 0 && tab_bytes) {
+		const uint64_t keep = policy_evict_last();
+		mbar_expect_tx(tab_bar, tab_bytes);
+		for (uint32_t off = 0; off < front_smem; off += 16384)
+			tma_bulk_g2s(s_front + off, a.front + off, min(16384u, front_smem - off), tab_bar, keep);
+		for (uint32_t off = 0; off < f2_bytes; off += 16384)
+			tma_bulk_g2s(reinterpret_cast<uint8_t *>(s_f2) + off, reinterpret_cast<const uint8_t *>(a.filter2) + off,
+					min(16384u, f2_bytes - off), tab_bar, keep);
+	}
+
+	// this CTA's span of warp tiles; warp w takes tiles cta_lo + w, + W, ...
+	const uint64_t cta_lo = min(a.tile_lo + (uint64_t) blockIdx.x * a.tiles_per_cta, a.tile_hi);
+	const uint64_t cta_hi = min(cta_lo + a.tiles_per_cta, a.tile_hi);
+	const uint64_t first = cta_lo + warp;
+	const uint64_t stream_pol = policy_evict_first();
+
+	uint32_t tma_mask = 0, phase_mask = 0;
+	auto issue = [&](uint64_t t, uint32_t s) {
+		uint8_t *dst = bufs + s * kBufBytes;
+		if (tile_is_interior(a, t)) {
+			if (lane == 0) {
+				// the generic-proxy reads of this slot are done (__syncwarp before us): order
+				// them before the async-proxy write
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				mbar_expect_tx(&bars[s], kLoadBytes);
+				tma_bulk_g2s(dst, a.text16 + t * (uint64_t) kTile - kHalo, kLoadBytes, &bars[s], stream_pol);
+			}
+			tma_mask |= 1u << s;
+		} else {
+			load_tile_edge(a, t, dst);
+			tma_mask &= ~(1u << s);
+		}
+	};
+
+	for (uint32_t s = 0; s + 1 < stages; s++) {
+		const uint64_t t = first + (uint64_t) s * W;
+		if (t < cta_hi)
+			issue(t, s);
+	}
+	__syncwarp();
+
+	uint32_t badacc = 0;
+	Emitter em{&a, 0, 0, 0};
+	Front fr;
+	if (tab_bytes)
+		mbar_wait(tab_bar, 0);
+	fr.init(s_front, a);
+
+	uint32_t slot = 0;
+	for (uint64_t tile = first; tile < cta_hi; tile += W) {
+		{
+			const uint64_t pf = tile + (uint64_t) (stages - 1) * W;
+			uint32_t ps = slot + stages - 1;
+			if (ps >= stages)
+				ps -= stages;
+			if (pf < cta_hi)
+				issue(pf, ps);
+		}
+		if ((tma_mask >> slot) & 1u) {
+			mbar_wait(&bars[slot], (phase_mask >> slot) & 1u);
+			phase_mask ^= 1u << slot;
+		}
+		__syncwarp();
+
+		const uint8_t *buf = bufs + slot * kBufBytes;
+		fr.scan(a, buf + kHalo + lane * kLane, pk, badacc);
+
+		em.tile = tile;
+		const uint64_t tile_start = tile * (uint64_t) kTile;
+		if constexpr (EXACT) {
+			const uint64_t end_lo = a.report_lo; // first end position this scan reports (>= data_lo + m_min - 1)
+			const bool inner = tile_start >= end_lo && tile_start + kTile <= a.data_hi;
+			if (!inner) { // first / last tiles: drop ends outside [end_lo, data_hi)
+				const uint64_t cs = tile_start + (uint64_t) lane * kLane;
+				const uint32_t lo_s = cs >= end_lo ? 0u : (uint32_t) min((uint64_t) kLane, end_lo - cs);
+				const uint32_t hi_s = cs >= a.data_hi ? 0u : (uint32_t) min((uint64_t) kLane, a.data_hi - cs);
+				fr.mask_range(lo_s, hi_s);
+			}
+			const uint32_t cnt = fr.count();
+			if (__any_sync(kFull, cnt != 0)) {
+				const uint32_t incl = warp_incl_scan(cnt);
+				const uint32_t total = __shfl_sync(kFull, incl, 31);
+				if (a.want_positions) {
+					unsigned long long slot0 = 0;
+					if (lane == 0)
+						slot0 = atomicAdd(&a.ctl->work.cursor, (unsigned long long) total);
+					unsigned long long at = __shfl_sync(kFull, slot0, 0) + (incl - cnt);
+					uint32_t rank = incl - cnt;
+#pragma unroll
+					for (int g = 0; g < Front::kWords; g++) {
+						uint32_t w = fr.hw[g];
+						while (w) {
+							const int b = __ffs(w) - 1;
+							w &= w - 1;
+							if (at < a.cap)
+								a.staging[at] = encode_stage(tile, rank, lane * kLane + Front::sym_of(g, b));
+							at++;
+							rank++;
+						}
+					}
+				}
+				em.tile_rank += total;
+				em.warp_count += total;
+			}
+		} else {
+			__syncwarp(); // the 2-bit copy of the tile (pk) is complete
+			uint32_t cnt = fr.count();
+			while (__any_sync(kFull, cnt != 0)) {
+				// round: queue up to kQueueCap candidates in lane order, then verify them densely
+				const uint32_t incl = warp_incl_scan(cnt);
+				const uint32_t excl = incl - cnt;
+				const uint32_t total = min(__shfl_sync(kFull, incl, 31), kQueueCap);
+				{
+					uint32_t k = excl, taken = 0;
+#pragma unroll
+					for (int g = 0; g < Front::kWords; g++) {
+						uint32_t w = fr.hw[g];
+						while (w && k < kQueueCap) {
+							const int b = __ffs(w) - 1;
+							w &= w - 1;
+							queue[k++] = (uint16_t) (lane * kLane + Front::sym_of(g, b));
+							taken++;
+						}
+						fr.hw[g] = w;
+					}
+					cnt -= taken;
+				}
+				__syncwarp();
+				const uint32_t probes = total * Front::kExpand;
+				for (uint32_t base = 0; base < probes; base += 32) {
+					const uint32_t i = base + lane;
+					uint32_t mult = 0, pos = 0;
+					if (i < probes) {
+						pos = (uint32_t) queue[i / Front::kExpand] + (i % Front::kExpand);
+						const uint32_t key = Front::key_at(a, buf, pk, pos);
+						const uint32_t i2 = (uint32_t) (key * a.prm.f2_mult) >> a.prm.f2_sh;
+						if ((s_f2[i2 >> 5] >> (i2 & 31)) & 1u)
+							mult = verify_window(a, key, tile_start + pos);
+					}
+					em.emit(mult, pos);
+				}
+				__syncwarp();
+			}
+		}
+		em.end_tile();
+		__syncwarp(); // every lane is done with this slot (and pk / queue) before it is refilled
+		slot = slot + 1 == stages ? 0 : slot + 1;
+	}
+
+	// ---- per-warp totals
+	Work *wk = &a.ctl->work;
+	if (lane == 0 && em.warp_count)
+		atomicAdd(&wk->count, em.warp_count);
+	if constexpr (Front::kPacked) {
+		badacc &= 0xFCFCFCFCu;
+		if (__any_sync(kFull, badacc != 0) && lane == 0)
+			atomicOr(&wk->bad_text, 1u);
+	}
+
+	// ---- order: staged matches -> sorted positions
+	if (a.want_positions) {
+		__syncthreads();
+		// exclusive prefix of the per-tile counts inside this CTA's span (in place)
+		const uint32_t n_b = (uint32_t) (cta_hi - cta_lo);
+		uint32_t carry = 0;
+		for (uint32_t base = 0; base < n_b; base += THREADS) {
+			const uint32_t i = base + threadIdx.x;
+			const uint32_t v = i < n_b ? __ldcg(a.tile_count + cta_lo + i) : 0u;
+			const uint32_t incl = warp_incl_scan(v);
+			if (lane == 31)
+				s_scan[warp] = incl;
+			__syncthreads();
+			if (warp == 0) {
+				const uint32_t x = lane < W ? s_scan[lane] : 0u;
+				const uint32_t xi = warp_incl_scan(x);
+				s_scan[lane] = xi - x;
+				if (lane == 31)
+					s_scan[32] = xi;
+			}
+			__syncthreads();
+			if (i < n_b)
+				a.tile_count[cta_lo + i] = carry + s_scan[warp] + incl - v;
+			carry += s_scan[32];
+			__syncthreads();
+		}
+		if (threadIdx.x == 0)
+			a.cta_total[blockIdx.x] = carry;
+
+		grid_barrier(&wk->arrived);
+
+		// span bases: exclusive prefix of the per-CTA totals (the ring buffers are free now)
+		unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_warps);
+		if (warp == 0) {
+			unsigned long long run = a.append ? __ldcg(&a.ctl->result.written) : 0ull;
+			for (uint32_t b0 = 0; b0 < gridDim.x; b0 += 32) {
+				const uint32_t b = b0 + lane;
+				const unsigned long long v = b < gridDim.x ? __ldcg(a.cta_total + b) : 0ull;
+				unsigned long long incl = v;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const unsigned long long t = __shfl_up_sync(kFull, incl, d);
+					if ((int) lane >= d)
+						incl += t;
+				}
+				if (b < gridDim.x)
+					s_base[b] = run + incl - v;
+				run += __shfl_sync(kFull, incl, 31);
+			}
+		}
+		__syncthreads();
+		const unsigned long long cursor = __ldcg(&wk->cursor);
+		const uint64_t staged = cursor < a.cap ? cursor : a.cap;
+		const uint64_t stride = (uint64_t) gridDim.x * THREADS;
+		for (uint64_t i = (uint64_t) blockIdx.x * THREADS + threadIdx.x; i < staged; i += stride) {
+			const uint64_t e = __ldcg(a.staging + i);
+			const uint64_t tile = e >> (kRankBits + kPosBits);
+			const uint32_t rank = (uint32_t) (e >> kPosBits) & ((1u << kRankBits) - 1);
+			const uint32_t pos = (uint32_t) e & ((1u << kPosBits) - 1);
+			const uint64_t owner = (tile - a.tile_lo) / a.tiles_per_cta;
+			const uint64_t at = s_base[owner] + __ldcg(a.tile_count + tile) + rank;
+			if (at < a.cap)
+				a.positions[at] = tile * kTile + pos - a.data_lo;
+		}
+	}
+
+	// ---- publish: the last CTA out folds the working counters into the result and clears them
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const unsigned int ticket = atomicAdd(&wk->done, 1u);
+		if (ticket == gridDim.x - 1) {
+			__threadfence();
+			Result *res = &a.ctl->result;
+			const unsigned long long cnt = __ldcg(&wk->count), cur = __ldcg(&wk->cursor);
+			const unsigned int bad = __ldcg(&wk->bad_text);
+			unsigned long long r_count = 0, r_written = 0;
+			unsigned int r_bad = 0, r_ovf = 0;
+			if (a.append) {
+				r_count = res->count;
+				r_written = res->written;
+				r_bad = res->bad_text;
+				r_ovf = res->overflow;
+			}
+			r_count += cnt;
+			if (a.want_positions) {
+				if (r_written + cur > a.cap) {
+					r_ovf = 1;
+					r_written = a.cap;
+				} else
+					r_written += cur;
+			}
+			res->count = r_count;
+			res->written = r_written;
+			res->bad_text = r_bad | bad;
+			res->overflow = r_ovf;
+			wk->count = 0;
+			wk->cursor = 0;
+			wk->bad_text = 0;
+			wk->arrived = 0;
+			wk->done = 0;
+		}
+	}
+}
+
+// ------------------------------------------------------------ launch helper
+template <class Front, bool EXACT, int THREADS>
+static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid, cudaStream_t st) {
+	auto kern = scan_kernel<Front, EXACT, THREADS>;
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if (e != cudaSuccess)
+		return e;
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(THREADS);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeCooperative; // the grid barrier needs every CTA resident
+	attr[0].val.cooperative = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+template <class Front, bool EXACT>
+static cudaError_t launch_front(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st) {
+	switch (threads) {
+	case 512: return launch_shape<Front, EXACT, 512>(a, smem, grid, st);
+	case 384: return launch_shape<Front, EXACT, 384>(a, smem, grid, st);
+	case 256: return launch_shape<Front, EXACT, 256>(a, smem, grid, st);
+	case 128: return launch_shape<Front, EXACT, 128>(a, smem, grid, st);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+} // namespace acwm

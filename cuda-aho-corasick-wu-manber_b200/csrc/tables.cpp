@@ -254,7 +254,7 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 		std::string &err) {
 	acwm_scan_params &prm = c.prm;
 	const uint32_t m = ps.m_min;
-	const uint32_t Dmax = std::min<uint32_t>(m, kHaloSyms);
+	const uint32_t Dmax = std::min<uint32_t>(m, kMaxDepthPacked);
 	// cost model (lane-instructions per symbol): 7 per DFA lookup, ~25 per verified candidate
 	double best_cost = 1e30;
 	uint32_t bestK = 0, bestD = 0;
@@ -330,12 +330,12 @@ static int compile_ac_bytes(const PatternSet &ps, const acwm_options &opts, uint
 	c.symclass.resize(256);
 	for (uint32_t b = 0; b < 256; b++)
 		c.symclass[b] = (uint8_t) std::min<uint32_t>(b, std::min<uint32_t>(ps.alphabet, 255));
-	const uint32_t Dmax = std::min<uint32_t>(m, kHaloBytes);
+	const uint32_t Dmax = std::min<uint32_t>(m, kMaxDepthBytes);
 	double best_cost = 1e30;
 	uint32_t bestD = 0;
 	bool best_smem = true;
 	uint32_t d_lo = 1, d_hi = std::min<uint32_t>(Dmax, 8);
-	if (m <= kHaloBytes && m > d_hi)
+	if (m <= kMaxDepthBytes && m > d_hi)
 		d_hi = m; // also try the exact automaton
 	if (opts.force_depth)
 		d_lo = d_hi = std::min<uint32_t>(std::max<uint32_t>(opts.force_depth, 1), Dmax);
@@ -472,7 +472,7 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 	prm.m_min = ps.m_min;
 	prm.m_max = ps.m_max;
 	uint32_t budget = opts.smem_table_budget ? opts.smem_table_budget : kDefaultTableBudget;
-	const uint32_t hard_cap = kMaxSmem - kSmemReserve - (packed ? 8 * kWarpSmemPacked : 4 * kWarpSmemBytes);
+	const uint32_t hard_cap = kMaxSmem - kSmemReserve - 4 * warp_smem_bytes(2);
 	budget = std::min(budget, hard_cap);
 	int rc;
 	if (algo == ACWM_ALGO_AC) {
@@ -493,13 +493,27 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 	}
 	if (rc != ACWM_OK)
 		return rc;
-	const uint32_t smem_tables = (out.info.table_in_smem ? (uint32_t) out.front.size() : 0)
-			+ (uint32_t) out.filter2.size() * 4;
-	const uint32_t threads = packed ? threads_for_tables_packed(smem_tables) : threads_for_tables_bytes(smem_tables);
-	if (!threads) {
+	// tables are rounded up to 16 bytes each in shared memory
+	const uint32_t smem_tables16 = (out.info.table_in_smem ? (((uint32_t) out.front.size() + 15u) & ~15u) : 0)
+			+ (((uint32_t) out.filter2.size() * 4 + 15u) & ~15u);
+	LaunchShape shape = shape_for_tables(smem_tables16);
+	if (opts.force_threads || opts.force_stages) { // tuning / tests
+		LaunchShape want{opts.force_threads ? opts.force_threads / 32 : shape.warps,
+				opts.force_stages ? opts.force_stages : shape.stages};
+		const bool ok = (want.warps == 16 || want.warps == 12 || want.warps == 8 || want.warps == 4)
+				&& want.warps * 32 == (opts.force_threads ? opts.force_threads : want.warps * 32)
+				&& want.stages >= 2 && want.stages <= kMaxStages && shape_fits(smem_tables16, want);
+		if (!ok) {
+			err = "forced launch shape (threads / stages) not available for this table size";
+			return ACWM_ERR_INVALID;
+		}
+		shape = want;
+	}
+	if (!shape.warps) {
 		err = "scan tables exceed shared memory";
 		return ACWM_ERR_UNSUPPORTED;
 	}
+	const uint32_t threads = shape.warps * 32;
 	acwm_info &inf = out.info;
 	inf.algo = (uint32_t) algo;
 	inf.alphabet = ps.alphabet;
@@ -514,7 +528,8 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 	inf.n_rows = prm.n_rows;
 	inf.n_states = (algo == ACWM_ALGO_AC) ? full_trie_states(ps, ps.alphabet) : 0;
 	inf.threads = threads;
-	inf.smem_bytes = smem_tables + (threads / 32) * (packed ? kWarpSmemPacked : kWarpSmemBytes) + kSmemReserve;
+	inf.stages = shape.stages;
+	inf.smem_bytes = smem_tables16 + shape.warps * warp_smem_bytes(shape.stages) + kSmemReserve;
 	inf.table_bytes = out.front.size() + out.filter2.size() * 4 + out.bucket_start.size() * 4
 			+ out.entries.size() * sizeof(acwm_ventry) + ps.bytes.size();
 	return ACWM_OK;

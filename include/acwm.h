@@ -65,8 +65,9 @@ typedef struct acwm_options {
 	uint32_t force_stride;      /* AC: symbols per DFA lookup (1,2,3); WM: sampling stride (1,2,4,8,16); 0 = auto */
 	uint32_t force_depth;       /* AC: truncate the automaton at this depth (candidates are verified); 0 = auto */
 	uint32_t force_bytes_path;  /* 1 = use the byte-per-symbol kernels even when alphabet <= 4 */
-	uint32_t force_threads;     /* threads per CTA of the scan kernel (tuning); 0 = auto */
-	uint32_t reserved[3];
+	uint32_t force_threads;     /* threads per CTA of the scan kernel: 128/256/384/512 (tuning); 0 = auto */
+	uint32_t force_stages;      /* ring depth of the per-warp TMA tile pipeline: 2..4 (tuning); 0 = auto */
+	uint32_t reserved[2];
 } acwm_options;
 
 /* What the builder chose; for reports and tests. */
@@ -81,7 +82,8 @@ typedef struct acwm_info {
 	uint32_t table_in_smem; /* 1: front-end table lives in shared memory, 0: global/L2 (access-policy window) */
 	uint32_t smem_bytes;    /* dynamic shared memory per CTA of the scan kernel */
 	uint64_t table_bytes;   /* bytes of device tables */
-	uint32_t threads, reserved;
+	uint32_t threads;       /* threads per CTA of the scan kernel */
+	uint32_t stages;        /* tiles in flight per warp (TMA ring depth) */
 } acwm_info;
 
 /* ------------------------------ native API ------------------------------ */

@@ -19,8 +19,8 @@ st = torch.cuda.current_stream().cuda_stream
 sizes = [int(x) for x in os.environ.get("TUNE_MIB", "128,1024").split(",")]
 wls = os.environ.get("TUNE_WL", "c2,c1,c2ac,c1wm").split(",")
 variants = {  # workload -> list of option dicts
-    "packed": [dict(force_threads=t) for t in (1024, 768, 512)],
-    "bytes": [dict(force_threads=t) for t in (512, 384, 256)],
+    "packed": [dict(force_threads=t, force_stages=st) for t in (512, 384, 256) for st in (2, 3)],
+    "bytes": [dict(force_threads=t, force_stages=st) for t in (512, 384, 256) for st in (2, 3)],
 }
 log("workload,text_mib,opts,stride,depth,exact,threads,smem,scan_us,finalize_us,GBps,frac_measured,count")
 texts = {}
@@ -31,7 +31,7 @@ for wl in wls:
     pats, m_max = bench.make_patterns(dg, text0, wl)
     extra = []
     if wl == "c1":
-        extra = [dict(force_stride=2), dict(force_stride=2, force_threads=512)]
+        extra = [dict(force_stride=2), dict(force_threads=256, force_stages=4)]
     if wl == "c2":
         extra = [dict(force_stride=4), dict(force_stride=16)]
     family = "packed" if alphabet <= 4 else "bytes"
@@ -61,6 +61,6 @@ for wl in wls:
                     ss.append(a); ff.append(b)
             scan = float(np.median(ss)); fin = float(np.median(ff))
             gbps = (mib << 20) / scan / 1e9
-            log(wl, mib, json.dumps(opts).replace(",", ";"), inf["stride"], inf["depth"], inf["exact_front"], inf["threads"],
+            log(wl, mib, json.dumps(opts).replace(",", ";"), inf["stride"], inf["depth"], inf["exact_front"], f'{inf["threads"]}x{inf["stages"]}',
                 inf["smem_bytes"], f"{scan*1e6:.1f}", f"{fin*1e6:.1f}", f"{gbps:.1f}", f"{gbps/6543.1:.3f}", cnt)
             mt.close()

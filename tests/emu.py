@@ -83,35 +83,43 @@ class Emulator:
 
     # ------------------------------------------------------------ front ends
     def _ac_hits(self, sym, chunk, K_bits, cols_of):
-        """Generic chunked DFA walk; returns sorted hit positions (may include e >= n)."""
+        """Generic chunked DFA walk; returns sorted hit positions (may include e >= n).
+        Mirrors FrontAC::scan / FrontACB::scan: the in-chunk strides start `off` symbols in
+        front of the chunk so that they end exactly at the chunk end, preceded by the
+        warm-up strides that bring the state up to date (depth-1 symbols of history)."""
         p = self.p
         K = p.stride
         D = p.depth
         n = sym.size
         nchunks = (n + chunk - 1) // chunk
-        wu = K * ((D - 1 + K - 1) // K)
+        off = (K - chunk % K) % K
+        need = D - 1
+        nwu = (need - off + K - 1) // K if need > off else 0
+        hist = off + K * nwu
         ent_bytes = 2 if self.info["table_in_smem"] else 4
         tab = self.front.view(np.uint16 if ent_bytes == 2 else np.uint32).astype(np.int64)
         cols = cols_of
-        lo = -wu
         total = nchunks * chunk
-        ext = np.zeros(total + wu, np.int64)
-        ext[wu:wu + n] = sym
+        ext = np.zeros(total + hist, np.int64)
+        ext[hist:hist + n] = sym
         starts = np.arange(nchunks, dtype=np.int64) * chunk
         state = np.zeros(nchunks, np.int64)
         hits = []
-        for t in range(lo // K, chunk // K):
+        for t in range(-nwu, (chunk + off) // K):
+            first = -off + K * t  # chunk-relative symbol of this stride's first symbol
             idx = np.zeros(nchunks, np.int64)
             for i in range(K):
-                idx |= ext[starts + wu + K * t + i] << (K_bits * i)
+                idx |= ext[starts + hist + first + i] << (K_bits * i)
             ent = tab[state * cols + idx]
             state = ent >> K
             h = ent & ((1 << K) - 1)
             if t >= 0 and h.any():
                 for i in range(K):
+                    if first + i < 0:
+                        continue  # belongs to the previous lane
                     sel = np.nonzero((h >> i) & 1)[0]
                     if sel.size:
-                        hits.append(starts[sel] + K * t + i)
+                        hits.append(starts[sel] + first + i)
         if not hits:
             return np.zeros(0, np.int64)
         return np.sort(np.concatenate(hits))
@@ -129,14 +137,14 @@ class Emulator:
             sym = text.astype(np.int64)
             win = self._win16(text)
             if p.algo == acwm.AC:
-                hits = self._ac_hits(sym, 192, 2, 1 << (2 * p.stride))
+                hits = self._ac_hits(sym, 112, 2, 1 << (2 * p.stride))
                 hits = hits[(hits >= m_min - 1) & (hits < n)]
                 if p.exact_front:
                     return int(hits.size), hits.astype(np.uint64)
                 ends = hits
             else:
                 s = p.stride
-                cpos = np.arange(0, ((n + 191) // 192) * 192, s, dtype=np.int64)
+                cpos = np.arange(0, ((n + 111) // 112) * 112, s, dtype=np.int64)
                 cin = cpos[cpos < n]
                 v = np.zeros(cpos.size, np.uint64)
                 v[:cin.size] = win[cin]

@@ -66,22 +66,15 @@ def test_empty_text(acwm, torch_cuda):
     assert count == 0 and pos.size == 0
 
 
-@pytest.mark.parametrize("threads", [256, 512, 768, 1024])
-def test_thread_variants_packed(acwm, oracle, torch_cuda, threads):
-    for cname in ("c1_ac_dna_p100_m8", "c2_wm_dna_p1000_m16", "ac_dna_depth5"):
+@pytest.mark.parametrize("threads,stages", [(128, 2), (256, 3), (384, 2), (512, 2), (256, 4), (384, 3)])
+def test_launch_shape_variants(acwm, oracle, torch_cuda, threads, stages):
+    """Every (warps, ring depth) shape of the scan kernel gives the same matches."""
+    for cname in ("c1_ac_dna_p100_m8", "c2_wm_dna_p1000_m16", "ac_dna_depth5", "wm_ascii_p1000_m8",
+                  "ac_protein_p100_m6"):
         case = next(c for c in RANDOM_CASES if c[0] == cname)
         name, algo, alphabet, p, m, n, opts = case
         pats, text = make_case(case)
-        _check(acwm, oracle, algo, pats, alphabet, text, force_threads=threads, **opts).close()
-
-
-@pytest.mark.parametrize("threads", [128, 256, 384, 512])
-def test_thread_variants_bytes(acwm, oracle, torch_cuda, threads):
-    for cname in ("wm_ascii_p1000_m8", "ac_protein_p100_m6"):
-        case = next(c for c in RANDOM_CASES if c[0] == cname)
-        name, algo, alphabet, p, m, n, opts = case
-        pats, text = make_case(case)
-        _check(acwm, oracle, algo, pats, alphabet, text, force_threads=threads, **opts).close()
+        _check(acwm, oracle, algo, pats, alphabet, text, force_threads=threads, force_stages=stages, **opts).close()
 
 
 def test_device_resident_unaligned_and_report_from(acwm, oracle, torch_cuda):
@@ -93,7 +86,7 @@ def test_device_resident_unaligned_and_report_from(acwm, oracle, torch_cuda):
         mt = acwm.Matcher(algo, pats, alphabet, **opts).upload(pos_capacity=text.size)
         d_all = torch.from_numpy(text).cuda()
         st = torch.cuda.current_stream().cuda_stream
-        for off, ln in ((0, text.size), (1, 70_001), (5, 6144 * 3), (13, 50_000), (16, 3584 * 5 + 3), (31, 777)):
+        for off, ln in ((0, text.size), (1, 70_001), (5, 3584 * 3), (13, 50_000), (16, 3584 * 5 + 3), (31, 777)):
             sub = d_all[off:off + ln]
             mt.scan_tensor(sub)
             count, pos, _ = mt.fetch(cap=text.size, stream=st)
@@ -237,7 +230,7 @@ def test_multi_gib_text_positions_beyond_32_bits(acwm, torch_cuda):
     pats = rng.integers(0, 4, (64, 24), dtype=np.uint8)
     # ends on both sides of a warp-tile edge and of the 2^32 boundary; >= 24 apart so the planted
     # windows do not overwrite each other
-    plant = [23, 6143, 6144 + 30, 2 * 6144, (1 << 32) - 1, (1 << 32) + 29, n - 1]
+    plant = [23, 3583, 3584 + 30, 2 * 3584, (1 << 32) - 1, (1 << 32) + 29, n - 1]
     for k, e in enumerate(plant):
         d_text[e - 23:e + 1] = torch.from_numpy(pats[k]).cuda()
     st = torch.cuda.current_stream().cuda_stream
