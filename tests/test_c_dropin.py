@@ -1,0 +1,49 @@
+"""The C integration example (examples/smatcher_main.c, the driver INTEGRATION.md shows):
+plain C, the reference's own call sequence (main.c:125-157, 268-298, 582-648), linked
+against libacwm_b200.so.  CPU: it compiles and links with gcc against include/acwm.h.
+GPU: it runs on files written here and prints the oracle's counts in the reference's
+own report format."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from cases import RANDOM_CASES, make_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "examples", "smatcher_main")
+
+
+def _build(acwm):
+    pkg = os.path.dirname(acwm.LIB_PATH)
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-I",
+                    os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "smatcher_main.c"), "-L", pkg,
+                    "-lacwm_b200", "-Wl,-rpath," + pkg, "-o", EXE], check=True)
+
+
+def test_c_driver_compiles_and_links_as_plain_c(acwm):
+    _build(acwm)
+    out = subprocess.run(["ldd", EXE], capture_output=True, text=True, check=True).stdout
+    assert "libacwm_b200.so" in out and "not found" not in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", [0, 1])
+def test_c_driver_prints_oracle_counts(acwm, oracle, tmp_path, idx):
+    _build(acwm)
+    case = RANDOM_CASES[idx]
+    name, algo, alphabet, p, m, n, opts = case
+    pats, text = make_case(case)
+    want = oracle.set_search(pats, text)["count"]
+    tf, pf = tmp_path / "text.bin", tmp_path / "pattern.bin"
+    text.tofile(tf)
+    np.ascontiguousarray(pats).tofile(pf)
+    out = subprocess.run([EXE, "ac" if algo == acwm.AC else "wm", "-m", str(m), "-n", str(text.size), "-p_size",
+                          str(p), "-alphabet", str(alphabet), "-text", str(tf), "-pattern", str(pf)],
+                         capture_output=True, text=True, check=True, timeout=300).stdout
+    first = "search_ac matches" if algo == acwm.AC else "search_wm2 matches"
+    assert int(re.search(first + r" \t(\d+)\t", out).group(1)) == want
+    assert int(re.search(r"Kernel 5 matches \t(\d+)\t", out).group(1)) == want
+    assert int(re.search(r"Total results: (\d+)\.", out).group(1)) == want
