@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libacwm_b200.so")
 AC, WM = 0, 1
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_OVERFLOW, ERR_BAD_TEXT = range(7)
 
-BLOB_FRONT, BLOB_FILTER2, BLOB_BUCKET_START, BLOB_ENTRIES, BLOB_PATTERNS, BLOB_PARAMS, BLOB_SYMCLASS = range(7)
+BLOB_FRONT, BLOB_FILTER2, BLOB_BUCKET_START, BLOB_ENTRIES, BLOB_PATTERNS, BLOB_PARAMS, BLOB_SYMCLASS, BLOB_RMASK = range(8)
 
 
 class AcwmError(RuntimeError):
@@ -38,7 +38,7 @@ class AcwmError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("smem_table_budget", C.c_uint32), ("force_stride", C.c_uint32), ("force_depth", C.c_uint32),
                 ("force_bytes_path", C.c_uint32), ("force_threads", C.c_uint32), ("force_stages", C.c_uint32),
-                ("reserved", C.c_uint32 * 2)]
+                ("force_f2_bits", C.c_uint32), ("force_r_bits", C.c_uint32)]
 
 
 class Info(C.Structure):
@@ -55,7 +55,8 @@ class ScanParams(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in
                 ("algo", "packed2bit", "alphabet", "m_min", "m_max", "stride", "depth", "exact_front", "n_rows",
                  "f1_sh1", "f1_mult", "f1_sh2", "f1_words", "b2", "f2_mult", "f2_sh", "f2_words", "hb_mult",
-                 "hb_sh", "n_buckets", "n_entries", "n_classes")] + [("reserved", C.c_uint32 * 8)]
+                 "hb_sh", "n_buckets", "n_entries", "n_classes", "r_mult", "r_sh", "r_entries", "r_entry_bytes")] + \
+               [("reserved", C.c_uint32 * 4)]
 
 
 VENTRY_DTYPE = np.dtype([("key", "<u4"), ("len", "<u4"), ("offset", "<u8")])

@@ -54,7 +54,9 @@ static int ensure_positions(acwm_matcher *mt, uint64_t cap) {
 		cudaFree(mt->d_positions);
 	mt->d_staging = mt->d_positions = nullptr;
 	mt->pos_cap = 0;
-	CU(cudaMalloc((void **) &mt->d_staging, cap * 8));
+	// staging: one reservation block of slack per warp the widest grid can hold
+	mt->stage_cap = cap + (uint64_t) kStageBlock * 32 * (uint64_t) std::max(mt->sm_count, 1);
+	CU(cudaMalloc((void **) &mt->d_staging, mt->stage_cap * 8));
 	CU(cudaMalloc((void **) &mt->d_positions, cap * 8));
 	mt->pos_cap = cap;
 	return ACWM_OK;
@@ -87,6 +89,8 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	const Compiled &c = mt->c;
 	int rc;
 	if ((rc = dev_upload(&mt->d_front, c.front.data(), c.front.size())))
+		return rc;
+	if ((rc = dev_upload(&mt->d_rmask, c.rmask.data(), c.rmask.size())))
 		return rc;
 	if ((rc = dev_upload(&mt->d_filter2, c.filter2.data(), c.filter2.size() * 4)))
 		return rc;
@@ -147,6 +151,7 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.front = mt->d_front;
 	a.front_bytes = (uint32_t) c.front.size();
 	a.front_in_smem = c.info.table_in_smem;
+	a.rmask = mt->d_rmask;
 	a.filter2 = mt->d_filter2;
 	a.bucket_start = mt->d_bucket_start;
 	a.entries = mt->d_entries;
@@ -156,6 +161,7 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.staging = mt->d_staging;
 	a.positions = mt->d_positions;
 	a.cap = want_positions ? mt->pos_cap : 0;
+	a.stage_cap = want_positions ? mt->stage_cap : 0;
 	a.tile_count = mt->d_tile_count;
 	a.cta_total = mt->d_cta_total;
 	a.stages = c.info.stages;
@@ -382,6 +388,7 @@ void acwm_free(acwm_matcher *mt) {
 		cudaSetDevice(mt->device);
 		cudaFree(mt->d_front);
 		cudaFree(mt->d_filter2);
+		cudaFree(mt->d_rmask);
 		cudaFree(mt->d_bucket_start);
 		cudaFree(mt->d_entries);
 		cudaFree(mt->d_patterns);
@@ -441,6 +448,7 @@ int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_
 	case ACWM_BLOB_PATTERNS: *ptr = mt->ps.bytes.data(); *bytes = mt->ps.bytes.size(); break;
 	case ACWM_BLOB_PARAMS: *ptr = &c.prm; *bytes = sizeof(c.prm); break;
 	case ACWM_BLOB_SYMCLASS: *ptr = c.symclass.data(); *bytes = c.symclass.size(); break;
+	case ACWM_BLOB_RMASK: *ptr = c.rmask.data(); *bytes = c.rmask.size(); break;
 	default: return set_error(ACWM_ERR_INVALID, "unknown blob id");
 	}
 	return ACWM_OK;

@@ -16,35 +16,44 @@ constexpr uint32_t kLoadBytes = kHalo + kTile;      // one TMA bulk copy: 3648 B
 constexpr uint32_t kBufBytes = kLoadBytes + 16;     // + pad read (never used) by the last window
 constexpr uint32_t kMaxDepthPacked = 60;            // AC 2-bit path: warm-up (depth-1 + 2) must fit the halo
 constexpr uint32_t kMaxDepthBytes = 64;             // AC bytes path: warm-up depth-1 <= 63
-constexpr uint32_t kQueueCap = 256;                 // candidate queue entries per warp (uint16)
 constexpr uint32_t kPackWords = 1 + kTile / 16 + 3; // 2-bit copy of the tile (+16 symbols of history, + pad) = 228 words
 constexpr uint32_t kMaxStages = 4;
 
-// per-warp shared memory: ring of raw tiles, 2-bit copy of the current tile (verification
-// windows), candidate queue, one mbarrier per ring slot
-constexpr uint32_t warp_smem_bytes(uint32_t stages) {
-	return stages * kBufBytes + kPackWords * 4 + kQueueCap * 2 + kMaxStages * 8;
+// per-warp shared memory: ring of raw tiles, (2-bit path) 2-bit copy of the current tile for the
+// verification windows, one mbarrier + one tile id per ring slot
+constexpr uint32_t warp_smem_bytes(uint32_t stages, bool packed) {
+	return stages * kBufBytes + (packed ? kPackWords * 4 : 0) + kMaxStages * 16;
 }
 
 constexpr uint32_t kMaxSmem = 227 * 1024;
 constexpr uint32_t kSmemReserve = 1024;             // CTA-level scratch (barriers, finalize scan), alignment slack
 
-// Staging entry: [tile:28 | rank:22 | pos_in_tile:14]
+// Staging entry: [tile:28 | rank:22 | pos_in_tile:14]; all-ones = unused slot
 constexpr uint32_t kPosBits = 14, kRankBits = 22;
+constexpr uint32_t kStageBlock = 32;                // staging slots a warp reserves per atomic
 
-// (warps, stages) the scan kernel is launched with, in order of preference.
+// (warps, stages) the scan kernel is launched with, in order of preference.  The 2-bit path
+// copies a tile into registers first and refills its slot while it walks, so one slot per
+// warp already overlaps load and scan; the bytes path reads the raw tile throughout.
 struct LaunchShape {
 	uint32_t warps, stages;
 };
-constexpr LaunchShape kShapes[] = {{16, 3}, {16, 2}, {12, 3}, {12, 2}, {8, 3}, {8, 2}, {4, 2}};
+constexpr LaunchShape kShapesPacked[] = {{32, 1}, {24, 1}, {16, 2}, {16, 1}, {12, 2}, {12, 1}, {8, 2}, {8, 1}, {4, 2}, {4, 1}};
+constexpr LaunchShape kShapesBytes[] = {{16, 2}, {12, 2}, {8, 2}, {4, 2}};
 
-inline bool shape_fits(uint32_t table_bytes, LaunchShape s) {
-	return table_bytes + s.warps * warp_smem_bytes(s.stages) + kSmemReserve <= kMaxSmem;
+inline bool shape_fits(uint32_t table_bytes, LaunchShape s, bool packed) {
+	return table_bytes + s.warps * warp_smem_bytes(s.stages, packed) + kSmemReserve <= kMaxSmem;
 }
-inline LaunchShape shape_for_tables(uint32_t table_bytes) {
-	for (const LaunchShape &s : kShapes)
-		if (shape_fits(table_bytes, s))
-			return s;
+inline LaunchShape shape_for_tables(uint32_t table_bytes, bool packed) {
+	if (packed) {
+		for (const LaunchShape &s : kShapesPacked)
+			if (shape_fits(table_bytes, s, true))
+				return s;
+	} else {
+		for (const LaunchShape &s : kShapesBytes)
+			if (shape_fits(table_bytes, s, false))
+				return s;
+	}
 	return LaunchShape{0, 0};
 }
 

@@ -27,6 +27,7 @@ struct acwm_matcher {
 	int device = -1, sm_count = 0;
 	size_t l2_persist_max = 0, l2_window_max = 0;
 	uint8_t *d_front = nullptr;
+	uint8_t *d_rmask = nullptr;
 	uint32_t *d_filter2 = nullptr;
 	uint32_t *d_bucket_start = nullptr;
 	acwm_ventry *d_entries = nullptr;
@@ -34,7 +35,7 @@ struct acwm_matcher {
 	acwm::Control *d_ctl = nullptr;
 	acwm::Result *h_res = nullptr;
 	uint64_t *d_staging = nullptr, *d_positions = nullptr;
-	uint64_t pos_cap = 0;
+	uint64_t pos_cap = 0, stage_cap = 0;
 	uint32_t *d_tile_count = nullptr;
 	uint64_t tile_cap = 0;
 	unsigned long long *d_cta_total = nullptr;

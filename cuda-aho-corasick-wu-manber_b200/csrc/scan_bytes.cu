@@ -41,7 +41,9 @@ struct BytesKey {
 // one lane's 112-byte chunk: 7 groups of 16 bytes, each handed to the front end together
 // with the 16 bytes in front of it
 #define ACWM_SCAN_GROUPS()                                         \
-	__device__ __forceinline__ void scan(const ScanArgs &a, const uint8_t *chunk, uint32_t *, uint32_t &) { \
+	const uint8_t *chunk;                                          \
+	__device__ __forceinline__ void load(const ScanArgs &, const uint8_t *c, uint32_t *, uint32_t &) { chunk = c; } \
+	__device__ __forceinline__ void walk(const ScanArgs &a) {      \
 		begin(a, chunk);                                           \
 		uint4 prev = *reinterpret_cast<const uint4 *>(chunk - 16); \
 		uint4 c;                                                   \
@@ -63,7 +65,10 @@ struct FrontACB : BytesKey {
 	uint32_t ent, lognc, alpha;
 	uint32_t hw[kWords];
 
-	__device__ __forceinline__ void init(const uint8_t *smem_tab, const ScanArgs &a) {
+	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &, const uint8_t *, const uint32_t *, uint32_t) const {
+		return 1u;
+	}
+	__device__ __forceinline__ void init(const uint8_t *smem_tab, const uint8_t *, const ScanArgs &a) {
 		tab = IN_SMEM ? smem_tab : a.front;
 		lognc = 31 - __clz(a.prm.n_classes);
 		alpha = min(a.prm.alphabet, 255u);
@@ -124,7 +129,18 @@ struct FrontWMB : BytesKey {
 	uint32_t sh1, mult, sh2;
 	uint32_t hw[kWords];
 
-	__device__ __forceinline__ void init(const uint8_t *smem_tab, const ScanArgs &a) {
+	const uint8_t *rmk;
+	// offsets r < S at which some pattern holds the block ending at tile byte `pos`
+	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &a, const uint8_t *buf, const uint32_t *,
+			uint32_t pos) const {
+		if (S == 1)
+			return 1u;
+		const uint32_t blk = mix64(window8(buf, kHalo + pos) >> sh1);
+		const uint32_t ri = (uint32_t) (blk * a.prm.r_mult) >> a.prm.r_sh;
+		return S > 8 ? (uint32_t) reinterpret_cast<const uint16_t *>(rmk)[ri] : (uint32_t) rmk[ri];
+	}
+	__device__ __forceinline__ void init(const uint8_t *smem_tab, const uint8_t *rmask, const ScanArgs &a) {
+		rmk = rmask;
 		bm = reinterpret_cast<const uint32_t *>(smem_tab);
 		sh1 = a.prm.f1_sh1;
 		mult = a.prm.f1_mult;

@@ -41,6 +41,7 @@ struct ScanArgs {
 	const uint8_t *front;        // front-end table (global copy)
 	uint32_t front_bytes;
 	uint32_t front_in_smem;
+	const uint8_t *rmask;        // WM offset masks (global copy), r_entries * r_entry_bytes
 	const uint32_t *filter2;     // stage-2 bitmap (global copy)
 	const uint32_t *bucket_start;
 	const acwm_ventry *entries;
@@ -49,7 +50,8 @@ struct ScanArgs {
 	Control *ctl;
 	uint64_t *staging;           // [tile:28 | rank:22 | pos:14]
 	uint64_t *positions;         // sorted output
-	uint64_t cap;                // capacity of staging and of positions (entries)
+	uint64_t cap;                // capacity of positions (entries)
+	uint64_t stage_cap;          // capacity of staging: cap + one reservation block per warp of the grid
 	uint32_t *tile_count;        // matches per tile -> (in the epilogue) exclusive prefix within the owning CTA
 	unsigned long long *cta_total; // matches per CTA
 	uint32_t stages;             // ring depth of the per-warp tile pipeline
@@ -141,46 +143,49 @@ __device__ __forceinline__ void grid_barrier(unsigned int *arrived) {
 	__syncthreads();
 }
 
-// Warp-collective emission of matches found at `pos` (tile-relative) with
-// multiplicity `mult` (0 = none) per lane, lanes in ascending position order.
+// Warp-level staging of the matches of one tile.  A warp reserves staging slots in blocks
+// (one atomic per >= kStageBlock matches instead of one per tile) and leaves the unused
+// tail of its last block marked with all-ones.
 struct Emitter {
 	const ScanArgs *a;
 	uint64_t tile;
-	uint32_t tile_rank;
 	unsigned long long warp_count;
+	unsigned long long blk_ptr, old_ptr, new_ptr;
+	uint32_t blk_left, old_left;
 
-	__device__ __forceinline__ void emit(uint32_t mult, uint32_t pos) {
-		const unsigned ball = __ballot_sync(kFull, mult != 0);
-		if (!ball)
-			return;
-		uint32_t excl, total;
-		if (__all_sync(kFull, mult <= 1)) {
-			excl = __popc(ball & ((1u << lane_id()) - 1));
-			total = __popc(ball);
-		} else {
-			const uint32_t incl = warp_incl_scan(mult);
-			excl = incl - mult;
-			total = __shfl_sync(kFull, incl, 31);
-		}
-		if (a->want_positions) {
-			unsigned long long slot0 = 0;
+	// warp-uniform: make room for `total` entries of the current tile
+	__device__ __forceinline__ void reserve(uint32_t total) {
+		old_ptr = blk_ptr;
+		old_left = blk_left;
+		new_ptr = 0;
+		if (total > blk_left) {
+			const uint32_t extra = total - blk_left;
+			const uint32_t grab = max(extra, kStageBlock);
+			unsigned long long p = 0;
 			if (lane_id() == 0)
-				slot0 = atomicAdd(&a->ctl->work.cursor, (unsigned long long) total);
-			slot0 = __shfl_sync(kFull, slot0, 0);
-			for (uint32_t i = 0; i < mult; i++) {
-				const unsigned long long slot = slot0 + excl + i;
-				if (slot < a->cap)
-					a->staging[slot] = encode_stage(tile, tile_rank + excl + i, pos);
-			}
+				p = atomicAdd(&a->ctl->work.cursor, (unsigned long long) grab);
+			new_ptr = __shfl_sync(kFull, p, 0);
+			blk_ptr = new_ptr + extra;
+			blk_left = grab - extra;
+		} else {
+			blk_ptr += total;
+			blk_left -= total;
 		}
-		tile_rank += total;
+	}
+	// entry k (= rank in the tile) of the current reservation
+	__device__ __forceinline__ void put(uint32_t k, uint32_t pos) const {
+		const unsigned long long slot = k < old_left ? old_ptr + k : new_ptr + (k - old_left);
+		if (slot < a->stage_cap)
+			a->staging[slot] = encode_stage(tile, k, pos);
+	}
+	__device__ __forceinline__ void end_tile(uint32_t total) {
+		if (a->want_positions && lane_id() == 0)
+			a->tile_count[tile] = total;
 		warp_count += total;
 	}
-
-	__device__ __forceinline__ void end_tile() {
-		if (a->want_positions && lane_id() == 0)
-			a->tile_count[tile] = tile_rank;
-		tile_rank = 0;
+	__device__ __forceinline__ void finish() const {
+		if (a->want_positions && lane_id() < blk_left && blk_ptr + lane_id() < a->stage_cap)
+			a->staging[blk_ptr + lane_id()] = ~0ull;
 	}
 };
 

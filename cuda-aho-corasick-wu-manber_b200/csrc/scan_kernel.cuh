@@ -48,56 +48,74 @@ template <class Front, bool EXACT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant__ ScanArgs a) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	constexpr uint32_t W = THREADS / 32;
-	// [CTA scratch 1 KiB][front table][stage-2 bitmap][per-warp areas]
+	constexpr bool kPacked = Front::kPacked;
+	// [CTA scratch 1 KiB][front table][offset masks][stage-2 bitmap][per-warp areas]
 	uint64_t *tab_bar = reinterpret_cast<uint64_t *>(smem);
+	uint32_t *s_next = reinterpret_cast<uint32_t *>(smem + 16); // next unclaimed tile of this CTA's span
 	uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + 64); // 33 words
 	const uint32_t front_smem = a.front_in_smem ? ((a.front_bytes + 15u) & ~15u) : 0u;
+	const uint32_t rm_bytes = EXACT ? 0u : ((a.prm.r_entries * a.prm.r_entry_bytes + 15u) & ~15u);
 	const uint32_t f2_bytes = EXACT ? 0u : ((a.prm.f2_words * 4u + 15u) & ~15u);
 	uint8_t *s_front = smem + kSmemReserve;
-	uint32_t *s_f2 = reinterpret_cast<uint32_t *>(s_front + front_smem);
-	uint8_t *s_warps = s_front + front_smem + f2_bytes;
+	uint8_t *s_rmask = s_front + front_smem;
+	uint32_t *s_f2 = reinterpret_cast<uint32_t *>(s_rmask + rm_bytes);
+	uint8_t *s_warps = s_rmask + rm_bytes + f2_bytes;
 
 	const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
 	const uint32_t stages = a.stages;
-	uint8_t *wbase = s_warps + warp * warp_smem_bytes(stages);
+	uint8_t *wbase = s_warps + warp * warp_smem_bytes(stages, kPacked);
 	uint8_t *bufs = wbase;
 	uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + stages * kBufBytes);
-	uint16_t *queue = reinterpret_cast<uint16_t *>(pk + kPackWords);
-	uint64_t *bars = reinterpret_cast<uint64_t *>(queue + kQueueCap);
+	uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + stages * kBufBytes + (kPacked ? kPackWords * 4 : 0));
+	uint32_t *s_tid = reinterpret_cast<uint32_t *>(bars + kMaxStages); // span-relative tile index per ring slot
 
-	if (threadIdx.x == 0)
+	if (threadIdx.x == 0) {
 		mbar_init(tab_bar, 1);
+		*s_next = 0;
+	}
 	if (lane == 0)
 		for (uint32_t s = 0; s < stages; s++)
 			mbar_init(&bars[s], 1);
 	if (lane < 4)
 		for (uint32_t s = 0; s < stages; s++) // pad behind each buffer: read, never used
 			reinterpret_cast<uint32_t *>(bufs + s * kBufBytes + kLoadBytes)[lane] = 0;
-	if (lane < 3)
+	if (kPacked && lane < 3)
 		pk[kPackWords - 3 + lane] = 0;
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncthreads();
 
 	// tables: global -> shared with TMA bulk copies, overlapped with the first text tiles
-	const uint32_t tab_bytes = front_smem + f2_bytes;
+	const uint32_t tab_bytes = front_smem + rm_bytes + f2_bytes;
 	if (threadIdx.x == 0 && tab_bytes) {
 		const uint64_t keep = policy_evict_last();
 		mbar_expect_tx(tab_bar, tab_bytes);
 		for (uint32_t off = 0; off < front_smem; off += 16384)
 			tma_bulk_g2s(s_front + off, a.front + off, min(16384u, front_smem - off), tab_bar, keep);
+		for (uint32_t off = 0; off < rm_bytes; off += 16384)
+			tma_bulk_g2s(s_rmask + off, a.rmask + off, min(16384u, rm_bytes - off), tab_bar, keep);
 		for (uint32_t off = 0; off < f2_bytes; off += 16384)
 			tma_bulk_g2s(reinterpret_cast<uint8_t *>(s_f2) + off, reinterpret_cast<const uint8_t *>(a.filter2) + off,
 					min(16384u, f2_bytes - off), tab_bar, keep);
 	}
 
-	// this CTA's span of warp tiles; warp w takes tiles cta_lo + w, + W, ...
+	// this CTA's span of warp tiles; the warps claim its tiles one at a time (shared-memory ticket)
 	const uint64_t cta_lo = min(a.tile_lo + (uint64_t) blockIdx.x * a.tiles_per_cta, a.tile_hi);
 	const uint64_t cta_hi = min(cta_lo + a.tiles_per_cta, a.tile_hi);
-	const uint64_t first = cta_lo + warp;
+	const uint32_t n_b = (uint32_t) (cta_hi - cta_lo);
 	const uint64_t stream_pol = policy_evict_first();
 
 	uint32_t tma_mask = 0, phase_mask = 0;
-	auto issue = [&](uint64_t t, uint32_t s) {
+	// claim the next tile of the span for ring slot s and start loading it
+	auto refill = [&](uint32_t s) {
+		uint32_t idx = 0;
+		if (lane == 0) {
+			idx = atomicAdd(s_next, 1u);
+			s_tid[s] = idx;
+		}
+		idx = __shfl_sync(kFull, idx, 0);
+		if (idx >= n_b)
+			return;
+		const uint64_t t = cta_lo + idx;
 		uint8_t *dst = bufs + s * kBufBytes;
 		if (tile_is_interior(a, t)) {
 			if (lane == 0) {
@@ -114,30 +132,27 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		}
 	};
 
-	for (uint32_t s = 0; s + 1 < stages; s++) {
-		const uint64_t t = first + (uint64_t) s * W;
-		if (t < cta_hi)
-			issue(t, s);
-	}
+	for (uint32_t s = 0; s < stages; s++)
+		refill(s);
 	__syncwarp();
 
 	uint32_t badacc = 0;
-	Emitter em{&a, 0, 0, 0};
+	Emitter em;
+	em.a = &a;
+	em.tile = 0;
+	em.warp_count = 0;
+	em.blk_ptr = em.old_ptr = em.new_ptr = 0;
+	em.blk_left = em.old_left = 0;
 	Front fr;
 	if (tab_bytes)
 		mbar_wait(tab_bar, 0);
-	fr.init(s_front, a);
+	fr.init(s_front, s_rmask, a);
 
-	uint32_t slot = 0;
-	for (uint64_t tile = first; tile < cta_hi; tile += W) {
-		{
-			const uint64_t pf = tile + (uint64_t) (stages - 1) * W;
-			uint32_t ps = slot + stages - 1;
-			if (ps >= stages)
-				ps -= stages;
-			if (pf < cta_hi)
-				issue(pf, ps);
-		}
+	for (uint32_t slot = 0;; slot = slot + 1 == stages ? 0 : slot + 1) {
+		const uint32_t idx = s_tid[slot];
+		if (idx >= n_b)
+			break; // the span is exhausted (claims are handed out in ascending order)
+		const uint64_t tile = cta_lo + idx;
 		if ((tma_mask >> slot) & 1u) {
 			mbar_wait(&bars[slot], (phase_mask >> slot) & 1u);
 			phase_mask ^= 1u << slot;
@@ -145,10 +160,16 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		__syncwarp();
 
 		const uint8_t *buf = bufs + slot * kBufBytes;
-		fr.scan(a, buf + kHalo + lane * kLane, pk, badacc);
+		fr.load(a, buf + kHalo + lane * kLane, pk, badacc);
+		if constexpr (kPacked) { // the tile now lives in registers (+ pk): refill the slot while we walk
+			__syncwarp();
+			refill(slot);
+		}
+		fr.walk(a);
 
 		em.tile = tile;
 		const uint64_t tile_start = tile * (uint64_t) kTile;
+		uint32_t total = 0;
 		if constexpr (EXACT) {
 			const uint64_t end_lo = a.report_lo; // first end position this scan reports (>= data_lo + m_min - 1)
 			const bool inner = tile_start >= end_lo && tile_start + kTile <= a.data_hi;
@@ -161,79 +182,102 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			const uint32_t cnt = fr.count();
 			if (__any_sync(kFull, cnt != 0)) {
 				const uint32_t incl = warp_incl_scan(cnt);
-				const uint32_t total = __shfl_sync(kFull, incl, 31);
+				total = __shfl_sync(kFull, incl, 31);
 				if (a.want_positions) {
-					unsigned long long slot0 = 0;
-					if (lane == 0)
-						slot0 = atomicAdd(&a.ctl->work.cursor, (unsigned long long) total);
-					unsigned long long at = __shfl_sync(kFull, slot0, 0) + (incl - cnt);
-					uint32_t rank = incl - cnt;
+					em.reserve(total);
+					uint32_t k = incl - cnt;
 #pragma unroll
 					for (int g = 0; g < Front::kWords; g++) {
 						uint32_t w = fr.hw[g];
 						while (w) {
 							const int b = __ffs(w) - 1;
 							w &= w - 1;
-							if (at < a.cap)
-								a.staging[at] = encode_stage(tile, rank, lane * kLane + Front::sym_of(g, b));
-							at++;
-							rank++;
+							em.put(k++, lane * kLane + Front::sym_of(g, b));
 						}
 					}
 				}
-				em.tile_rank += total;
-				em.warp_count += total;
 			}
 		} else {
-			__syncwarp(); // the 2-bit copy of the tile (pk) is complete
-			uint32_t cnt = fr.count();
-			while (__any_sync(kFull, cnt != 0)) {
-				// round: queue up to kQueueCap candidates in lane order, then verify them densely
-				const uint32_t incl = warp_incl_scan(cnt);
-				const uint32_t excl = incl - cnt;
-				const uint32_t total = min(__shfl_sync(kFull, incl, 31), kQueueCap);
-				{
-					uint32_t k = excl, taken = 0;
+			if constexpr (kPacked)
+				__syncwarp(); // the 2-bit copy of the tile (pk) is complete
+			// every lane checks its own candidates: offset mask -> stage-2 bitmap -> buckets;
+			// survivors become bits of mw (chunk-relative end positions)
+			uint32_t mw0 = 0, mw1 = 0, mw2 = 0, mw3 = 0, multi = 0;
 #pragma unroll
-					for (int g = 0; g < Front::kWords; g++) {
-						uint32_t w = fr.hw[g];
-						while (w && k < kQueueCap) {
-							const int b = __ffs(w) - 1;
-							w &= w - 1;
-							queue[k++] = (uint16_t) (lane * kLane + Front::sym_of(g, b));
-							taken++;
-						}
-						fr.hw[g] = w;
-					}
-					cnt -= taken;
-				}
-				__syncwarp();
-				const uint32_t probes = total * Front::kExpand;
-				for (uint32_t base = 0; base < probes; base += 32) {
-					const uint32_t i = base + lane;
-					uint32_t mult = 0, pos = 0;
-					if (i < probes) {
-						pos = (uint32_t) queue[i / Front::kExpand] + (i % Front::kExpand);
-						const uint32_t key = Front::key_at(a, buf, pk, pos);
+			for (int g = 0; g < Front::kWords; g++) {
+				uint32_t w = fr.hw[g];
+				while (w) {
+					const int b = __ffs(w) - 1;
+					w &= w - 1;
+					const uint32_t c = Front::sym_of(g, b);
+					uint32_t rm = fr.probe_mask(a, buf, pk, lane * kLane + c);
+					while (rm) {
+						const uint32_t p = c + (uint32_t) (__ffs(rm) - 1);
+						rm &= rm - 1;
+						const uint32_t key = Front::key_at(a, buf, pk, lane * kLane + p);
 						const uint32_t i2 = (uint32_t) (key * a.prm.f2_mult) >> a.prm.f2_sh;
-						if ((s_f2[i2 >> 5] >> (i2 & 31)) & 1u)
-							mult = verify_window(a, key, tile_start + pos);
+						if ((s_f2[i2 >> 5] >> (i2 & 31)) & 1u) {
+							const uint32_t mult = verify_window(a, key, tile_start + lane * kLane + p);
+							if (mult) {
+								const uint32_t bit = 1u << (p & 31);
+								if (p < 32)
+									mw0 |= bit;
+								else if (p < 64)
+									mw1 |= bit;
+								else if (p < 96)
+									mw2 |= bit;
+								else
+									mw3 |= bit;
+								multi |= mult > 1;
+							}
+						}
 					}
-					em.emit(mult, pos);
 				}
-				__syncwarp();
+			}
+			// how many entries this lane emits (a position with several patterns ending there
+			// emits one entry per pattern: mixed-length sets only; recounted on demand)
+			auto mult_at = [&](uint32_t p) {
+				const uint32_t key = Front::key_at(a, buf, pk, lane * kLane + p);
+				return verify_window(a, key, tile_start + lane * kLane + p);
+			};
+			const uint32_t mw[4] = {mw0, mw1, mw2, mw3};
+			uint32_t cnt = __popc(mw0) + __popc(mw1) + __popc(mw2) + __popc(mw3);
+			if (multi) {
+				cnt = 0;
+#pragma unroll
+				for (int g = 0; g < 4; g++)
+					for (uint32_t w = mw[g]; w; w &= w - 1)
+						cnt += mult_at(32 * g + __ffs(w) - 1);
+			}
+			if (__any_sync(kFull, cnt != 0)) {
+				const uint32_t incl = warp_incl_scan(cnt);
+				total = __shfl_sync(kFull, incl, 31);
+				if (a.want_positions) {
+					em.reserve(total);
+					uint32_t k = incl - cnt;
+#pragma unroll
+					for (int g = 0; g < 4; g++)
+						for (uint32_t w = mw[g]; w; w &= w - 1) {
+							const uint32_t p = 32 * g + __ffs(w) - 1;
+							const uint32_t reps = multi ? mult_at(p) : 1u;
+							for (uint32_t i = 0; i < reps; i++)
+								em.put(k++, lane * kLane + p);
+						}
+				}
 			}
 		}
-		em.end_tile();
-		__syncwarp(); // every lane is done with this slot (and pk / queue) before it is refilled
-		slot = slot + 1 == stages ? 0 : slot + 1;
+		em.end_tile(total);
+		__syncwarp(); // every lane is done with this slot (and pk) before it is refilled / rewritten
+		if constexpr (!kPacked)
+			refill(slot);
 	}
+	em.finish();
 
 	// ---- per-warp totals
 	Work *wk = &a.ctl->work;
 	if (lane == 0 && em.warp_count)
 		atomicAdd(&wk->count, em.warp_count);
-	if constexpr (Front::kPacked) {
+	if constexpr (kPacked) {
 		badacc &= 0xFCFCFCFCu;
 		if (__any_sync(kFull, badacc != 0) && lane == 0)
 			atomicOr(&wk->bad_text, 1u);
@@ -243,7 +287,6 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	if (a.want_positions) {
 		__syncthreads();
 		// exclusive prefix of the per-tile counts inside this CTA's span (in place)
-		const uint32_t n_b = (uint32_t) (cta_hi - cta_lo);
 		uint32_t carry = 0;
 		for (uint32_t base = 0; base < n_b; base += THREADS) {
 			const uint32_t i = base + threadIdx.x;
@@ -291,10 +334,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		}
 		__syncthreads();
 		const unsigned long long cursor = __ldcg(&wk->cursor);
-		const uint64_t staged = cursor < a.cap ? cursor : a.cap;
+		const uint64_t staged = cursor < a.stage_cap ? cursor : a.stage_cap;
 		const uint64_t stride = (uint64_t) gridDim.x * THREADS;
 		for (uint64_t i = (uint64_t) blockIdx.x * THREADS + threadIdx.x; i < staged; i += stride) {
 			const uint64_t e = __ldcg(a.staging + i);
+			if (e == ~0ull)
+				continue; // unused tail of a warp's reservation
 			const uint64_t tile = e >> (kRankBits + kPosBits);
 			const uint32_t rank = (uint32_t) (e >> kPosBits) & ((1u << kRankBits) - 1);
 			const uint32_t pos = (uint32_t) e & ((1u << kPosBits) - 1);
@@ -325,11 +370,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			}
 			r_count += cnt;
 			if (a.want_positions) {
-				if (r_written + cur > a.cap) {
+				if (r_written + cnt > a.cap || cur > a.stage_cap) {
 					r_ovf = 1;
-					r_written = a.cap;
+					r_written = min(r_written + cnt, (unsigned long long) a.cap);
 				} else
-					r_written += cur;
+					r_written += cnt;
 			}
 			res->count = r_count;
 			res->written = r_written;
@@ -368,6 +413,8 @@ static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid,
 template <class Front, bool EXACT>
 static cudaError_t launch_front(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st) {
 	switch (threads) {
+	case 1024: return launch_shape<Front, EXACT, 1024>(a, smem, grid, st);
+	case 768: return launch_shape<Front, EXACT, 768>(a, smem, grid, st);
 	case 512: return launch_shape<Front, EXACT, 512>(a, smem, grid, st);
 	case 384: return launch_shape<Front, EXACT, 384>(a, smem, grid, st);
 	case 256: return launch_shape<Front, EXACT, 256>(a, smem, grid, st);

@@ -9,10 +9,11 @@
 //          one-symbol goto/failure walk of cuda/cuda_ac.cu:88-95.
 //   WM<S>  Wu-Manber block filter sampled every S symbols (SHIFT[block] < S as a
 //          bitmap).  Supersedes the divergent skip loop of cuda/cuda_wm.cu:136-176.
-// Hits of an exact AC automaton are matches; hits of a depth-truncated automaton and
-// WM candidates go through the stage-2 suffix bitmap and the bucket verification, which
-// read their 16-symbol windows from a 2-bit copy of the tile the lanes leave in shared
-// memory (7 STS per lane).
+// Once the chunk is in registers the warp refills its raw slot (TMA) and walks; one slot
+// per warp therefore overlaps load and scan.  Hits of an exact AC automaton are matches;
+// hits of a depth-truncated automaton and WM candidates are checked by the lane that found
+// them (offset mask -> stage-2 suffix bitmap -> buckets) on 16-symbol windows read from a
+// 2-bit copy of the tile the lanes leave in shared memory (7 STS per lane).
 #include <cstring>
 
 #include "scan_kernel.cuh"
@@ -80,10 +81,23 @@ struct FrontAC : PackedKey {
 
 	const uint8_t *tab; // shared-memory DFA
 	uint32_t ent;       // current entry (row << K | hits)
+	uint32_t nwu, hist; // warm-up strides / symbols of history they (and the first in-chunk stride) cover
+	uint32_t W[8];      // W[0] = the 16 symbols in front of the chunk, W[1..7] = the chunk
+	uint32_t H[3];      // long warm-up only: symbols -64..-17
 	uint32_t hw[kWords];
 
-	__device__ __forceinline__ void init(const uint8_t *table, const ScanArgs &) { tab = table; }
+	__device__ __forceinline__ void init(const uint8_t *table, const uint8_t *, const ScanArgs &a) {
+		tab = table;
+		// the state must have seen depth-1 symbols of history when the chunk starts; the first
+		// in-chunk stride covers kOff of them
+		const uint32_t need = a.prm.depth - 1;
+		nwu = need > (uint32_t) kOff ? (need - kOff + K - 1) / K : 0u;
+		hist = kOff + K * nwu; // <= 16: W[0] is enough; else up to 64 symbols of raw history
+	}
 	static __device__ __forceinline__ uint32_t sym_of(int g, int b) { return (uint32_t) (g * kGroupSyms + b - kOff); }
+	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &, const uint8_t *, const uint32_t *, uint32_t) const {
+		return 1u; // a hit of the truncated automaton is probed where it ends
+	}
 
 	__device__ __forceinline__ uint32_t step(uint32_t sym2) {
 		const uint32_t addr = ((ent << (K + 1)) & kRowMask) | sym2;
@@ -91,18 +105,22 @@ struct FrontAC : PackedKey {
 		return ent & kHitMask;
 	}
 
-	__device__ __forceinline__ void scan(const ScanArgs &a, const uint8_t *chunk, uint32_t *pk, uint32_t &badacc) {
-		uint32_t W[8];
+	__device__ __forceinline__ void load(const ScanArgs &, const uint8_t *chunk, uint32_t *pk, uint32_t &badacc) {
 		load_pack<!EXACT>(chunk, W, pk, badacc);
+		if (hist > 16) {
+			const uint4 *c4 = reinterpret_cast<const uint4 *>(chunk);
+			uint32_t dummy = 0;
+			H[0] = pack16(c4[-4], dummy);
+			H[1] = pack16(c4[-3], dummy);
+			H[2] = pack16(c4[-2], dummy);
+		}
+	}
+
+	__device__ __forceinline__ void walk(const ScanArgs &) {
 		ent = 0;
 #pragma unroll
 		for (int g = 0; g < kWords; g++)
 			hw[g] = 0;
-		// warm-up: the state must have seen depth-1 symbols of history when the chunk starts;
-		// the first in-chunk stride covers kOff of them
-		const uint32_t need = a.prm.depth - 1;
-		const uint32_t nwu = need > (uint32_t) kOff ? (need - kOff + K - 1) / K : 0u;
-		const uint32_t hist = kOff + K * nwu; // <= 16: from W[0]; else up to 64 symbols from the raw history
 		if (nwu) {
 			if (hist <= 16) {
 				uint32_t h = W[0] >> (32 - 2 * hist);
@@ -111,10 +129,7 @@ struct FrontAC : PackedKey {
 					h >>= 2 * K;
 				}
 			} else {
-				const uint4 *c4 = reinterpret_cast<const uint4 *>(chunk);
-				uint32_t dummy = 0;
-				const uint32_t h0 = pack16(c4[-4], dummy), h1 = pack16(c4[-3], dummy), h2 = pack16(c4[-2], dummy);
-				uint64_t lo = ((uint64_t) h1 << 32) | h0, hi = ((uint64_t) W[0] << 32) | h2;
+				uint64_t lo = ((uint64_t) H[1] << 32) | H[0], hi = ((uint64_t) W[0] << 32) | H[2];
 				const uint32_t sh = 128 - 2 * hist; // bits to drop from the front
 				if (sh >= 64) {
 					lo = hi >> (sh - 64);
@@ -175,20 +190,35 @@ struct FrontWM : PackedKey {
 	static constexpr int kExpand = S;
 
 	const uint32_t *bm; // shared-memory block bitmap
+	const uint8_t *rmk; // shared-memory offset masks
 	uint32_t sh1, mult, sh2;
+	uint32_t W[8];
 	uint32_t hw[kWords];
 
-	__device__ __forceinline__ void init(const uint8_t *table, const ScanArgs &a) {
+	__device__ __forceinline__ void init(const uint8_t *table, const uint8_t *rmask, const ScanArgs &a) {
 		bm = reinterpret_cast<const uint32_t *>(table);
+		rmk = rmask;
 		sh1 = a.prm.f1_sh1;
 		mult = a.prm.f1_mult;
 		sh2 = a.prm.f1_sh2;
 	}
 	static __device__ __forceinline__ uint32_t sym_of(int g, int b) { return (uint32_t) ((g * 32 + b) * S); }
 
-	__device__ __forceinline__ void scan(const ScanArgs &, const uint8_t *chunk, uint32_t *pk, uint32_t &badacc) {
-		uint32_t W[8];
+	// offsets r < S at which some pattern holds the block ending at tile symbol `pos`
+	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &a, const uint8_t *, const uint32_t *pk,
+			uint32_t pos) const {
+		if (S == 1)
+			return 1u;
+		const uint32_t blk = window16(pk, pos) >> sh1;
+		const uint32_t ri = (uint32_t) (blk * a.prm.r_mult) >> a.prm.r_sh;
+		return S > 8 ? (uint32_t) reinterpret_cast<const uint16_t *>(rmk)[ri] : (uint32_t) rmk[ri];
+	}
+
+	__device__ __forceinline__ void load(const ScanArgs &, const uint8_t *chunk, uint32_t *pk, uint32_t &badacc) {
 		load_pack<true>(chunk, W, pk, badacc);
+	}
+
+	__device__ __forceinline__ void walk(const ScanArgs &) {
 #pragma unroll
 		for (int g = 0; g < kWords; g++)
 			hw[g] = 0;

@@ -86,6 +86,7 @@ static uint32_t ceil_log2(uint64_t v) {
 static const uint32_t kMultF1 = 0x9E3779B1u;  // stage-1 block hash
 static const uint32_t kMultF2 = 0x85EBCA77u;  // stage-2 suffix hash
 static const uint32_t kMultHB = 0xC2B2AE3Du;  // bucket hash
+static const uint32_t kMultR = 0x27D4EB2Fu;   // offset-mask hash
 
 static inline void set_bit(std::vector<uint32_t> &bm, uint32_t idx) { bm[idx >> 5] |= 1u << (idx & 31); }
 
@@ -97,14 +98,17 @@ static uint32_t pattern_key(const PatternSet &ps, uint32_t j, bool packed, uint3
 }
 
 // Stage 2 (suffix bitmap) + verification buckets, shared by WM and truncated AC.
-static void build_verify(const PatternSet &ps, bool packed, Compiled &c) {
+static void build_verify(const PatternSet &ps, bool packed, const acwm_options &opts, Compiled &c) {
 	acwm_scan_params &prm = c.prm;
 	const uint32_t pd = ps.size();
 	const uint32_t b2 = packed ? std::min<uint32_t>(ps.m_min, 16) : std::min<uint32_t>(ps.m_min, 8);
 	prm.b2 = b2;
 	// stage-2 bitmap: direct index when the key space is small, hashed otherwise
 	const uint32_t key_bits = packed ? 2 * b2 : 32;
-	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 64), 13), 19);
+	// ~0.4 % of the probes pass: a pass costs dependent L2 loads (buckets), so it has to be rare
+	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 256), 13), 18);
+	if (opts.force_f2_bits)
+		f2bits = std::min<uint32_t>(std::max<uint32_t>(opts.force_f2_bits, 13), 19);
 	if (packed && key_bits <= f2bits) {
 		f2bits = std::max<uint32_t>(key_bits, 5);
 		prm.f2_mult = 1;
@@ -312,7 +316,7 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 	prm.exact_front = (bestD == m) ? 1 : 0;
 	prm.n_rows = n_rows;
 	if (!prm.exact_front)
-		build_verify(ps, true, c);
+		build_verify(ps, true, opts, c);
 	c.info.table_in_smem = 1;
 	return ACWM_OK;
 }
@@ -385,7 +389,7 @@ static int compile_ac_bytes(const PatternSet &ps, const acwm_options &opts, uint
 	prm.n_rows = n_rows;
 	prm.n_classes = ncols;
 	if (!prm.exact_front)
-		build_verify(ps, false, c);
+		build_verify(ps, false, opts, c);
 	c.info.table_in_smem = best_smem ? 1 : 0;
 	return ACWM_OK;
 }
@@ -415,8 +419,9 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 		const double space_bits = std::min<double>(B * sigma_bits, (double) max_fbits);
 		const double load = (double) s * pd / std::pow(2.0, space_bits);
 		const double rate = 1.0 - std::exp(-load);
-		// per symbol: 11/s for the sampled filter + `rate` stage-2 probes of ~12
-		const double cost = (packed ? 11.0 : 13.0) / s + rate * 12.0;
+		// per symbol: ~8 lane-instructions per sample + `rate` candidates per sample, each handled by its
+		// own lane while the rest of the warp waits (~150 lane-instruction slots)
+		const double cost = ((packed ? 8.0 : 10.0) + rate * 150.0) / s;
 		if (cost < best_cost - 1e-9) {
 			best_cost = cost;
 			bestS = s;
@@ -456,7 +461,28 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 	c.front_entry_bytes = 4;
 	c.front.resize((size_t) prm.f1_words * 4);
 	memcpy(c.front.data(), bm.data(), c.front.size());
-	build_verify(ps, packed, c);
+	// offset masks: a candidate block only has to be probed at the offsets r some pattern holds it at
+	if (s > 1) {
+		uint32_t rbits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 4), 10), 15);
+		if (opts.force_r_bits)
+			rbits = std::min<uint32_t>(std::max<uint32_t>(opts.force_r_bits, 10), 16);
+		prm.r_mult = kMultR;
+		prm.r_sh = 32 - rbits;
+		prm.r_entries = 1u << rbits;
+		prm.r_entry_bytes = s > 8 ? 2 : 1;
+		c.rmask.assign((size_t) prm.r_entries * prm.r_entry_bytes, 0);
+		for (uint32_t j = 0; j < pd; j++)
+			for (uint32_t r = 0; r < s; r++) {
+				const uint32_t v = packed ? pack2_tail(ps.pat(j), ps.len[j], B, r)
+										  : mix64to32(pack8_tail(ps.pat(j), ps.len[j], B, r));
+				const uint32_t ri = (uint32_t) (v * prm.r_mult) >> prm.r_sh;
+				if (prm.r_entry_bytes == 1)
+					c.rmask[ri] |= (uint8_t) (1u << r);
+				else
+					reinterpret_cast<uint16_t *>(c.rmask.data())[ri] |= (uint16_t) (1u << r);
+			}
+	}
+	build_verify(ps, packed, opts, c);
 	c.info.table_in_smem = 1;
 	return ACWM_OK;
 }
@@ -472,7 +498,7 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 	prm.m_min = ps.m_min;
 	prm.m_max = ps.m_max;
 	uint32_t budget = opts.smem_table_budget ? opts.smem_table_budget : kDefaultTableBudget;
-	const uint32_t hard_cap = kMaxSmem - kSmemReserve - 4 * warp_smem_bytes(2);
+	const uint32_t hard_cap = kMaxSmem - kSmemReserve - 4 * warp_smem_bytes(2, packed);
 	budget = std::min(budget, hard_cap);
 	int rc;
 	if (algo == ACWM_ALGO_AC) {
@@ -482,10 +508,10 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 			return ACWM_ERR_UNSUPPORTED;
 		}
 		// leave room for the stage-2 bitmap in case the automaton gets truncated
-		const uint32_t ac_budget = budget > 24 * 1024 ? budget - 16 * 1024 : budget;
+		const uint32_t ac_budget = budget > 64 * 1024 ? budget - 32 * 1024 : budget / 2;
 		rc = packed ? compile_ac_packed(ps, opts, ac_budget, out, err) : compile_ac_bytes(ps, opts, ac_budget, out, err);
 	} else if (algo == ACWM_ALGO_WM) {
-		const uint32_t wm_budget = std::min<uint32_t>(budget, 128 * 1024) * 3 / 4;
+		const uint32_t wm_budget = budget / 2; // stage-1 bitmap; the offset masks and the stage-2 bitmap take <= 32 KiB each
 		rc = compile_wm(ps, opts, packed, wm_budget, out, err);
 	} else {
 		err = "unknown algorithm id";
@@ -495,14 +521,16 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 		return rc;
 	// tables are rounded up to 16 bytes each in shared memory
 	const uint32_t smem_tables16 = (out.info.table_in_smem ? (((uint32_t) out.front.size() + 15u) & ~15u) : 0)
-			+ (((uint32_t) out.filter2.size() * 4 + 15u) & ~15u);
-	LaunchShape shape = shape_for_tables(smem_tables16);
+			+ (((uint32_t) out.rmask.size() + 15u) & ~15u) + (((uint32_t) out.filter2.size() * 4 + 15u) & ~15u);
+	LaunchShape shape = shape_for_tables(smem_tables16, packed);
 	if (opts.force_threads || opts.force_stages) { // tuning / tests
 		LaunchShape want{opts.force_threads ? opts.force_threads / 32 : shape.warps,
 				opts.force_stages ? opts.force_stages : shape.stages};
-		const bool ok = (want.warps == 16 || want.warps == 12 || want.warps == 8 || want.warps == 4)
+		const bool ok = (want.warps == 32 || want.warps == 24 || want.warps == 16 || want.warps == 12 || want.warps == 8
+								|| want.warps == 4)
 				&& want.warps * 32 == (opts.force_threads ? opts.force_threads : want.warps * 32)
-				&& want.stages >= 2 && want.stages <= kMaxStages && shape_fits(smem_tables16, want);
+				&& want.stages >= (packed ? 1u : 2u) && want.stages <= kMaxStages
+				&& shape_fits(smem_tables16, want, packed);
 		if (!ok) {
 			err = "forced launch shape (threads / stages) not available for this table size";
 			return ACWM_ERR_INVALID;
@@ -529,8 +557,8 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 	inf.n_states = (algo == ACWM_ALGO_AC) ? full_trie_states(ps, ps.alphabet) : 0;
 	inf.threads = threads;
 	inf.stages = shape.stages;
-	inf.smem_bytes = smem_tables16 + shape.warps * warp_smem_bytes(shape.stages) + kSmemReserve;
-	inf.table_bytes = out.front.size() + out.filter2.size() * 4 + out.bucket_start.size() * 4
+	inf.smem_bytes = smem_tables16 + shape.warps * warp_smem_bytes(shape.stages, packed) + kSmemReserve;
+	inf.table_bytes = out.front.size() + out.rmask.size() + out.filter2.size() * 4 + out.bucket_start.size() * 4
 			+ out.entries.size() * sizeof(acwm_ventry) + ps.bytes.size();
 	return ACWM_OK;
 }

@@ -34,6 +34,7 @@ struct Compiled {
 	acwm_scan_params prm{};
 	acwm_info info{};
 	std::vector<uint8_t> front;          // AC: uint16 (smem) or uint32 (global) DFA entries; WM: uint32 bitmap words
+	std::vector<uint8_t> rmask;          // WM, stride > 1: which offsets r < s a candidate block can sit at (uint8 / uint16)
 	std::vector<uint32_t> filter2;       // stage-2 suffix bitmap
 	std::vector<uint32_t> bucket_start;  // n_buckets + 1
 	std::vector<acwm_ventry> entries;
@@ -43,7 +44,7 @@ struct Compiled {
 
 // Geometry shared by the builder's cost model and the kernels.
 constexpr uint32_t kSmemPerSM = 227 * 1024;
-constexpr uint32_t kDefaultTableBudget = 144 * 1024;
+constexpr uint32_t kDefaultTableBudget = 128 * 1024;
 
 int normalize_patterns(const uint8_t *patterns, const uint32_t *lens, uint32_t m, uint32_t p, uint32_t alphabet,
 		PatternSet &out, std::string &err);

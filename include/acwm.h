@@ -65,9 +65,10 @@ typedef struct acwm_options {
 	uint32_t force_stride;      /* AC: symbols per DFA lookup (1,2,3); WM: sampling stride (1,2,4,8,16); 0 = auto */
 	uint32_t force_depth;       /* AC: truncate the automaton at this depth (candidates are verified); 0 = auto */
 	uint32_t force_bytes_path;  /* 1 = use the byte-per-symbol kernels even when alphabet <= 4 */
-	uint32_t force_threads;     /* threads per CTA of the scan kernel: 128/256/384/512 (tuning); 0 = auto */
-	uint32_t force_stages;      /* ring depth of the per-warp TMA tile pipeline: 2..4 (tuning); 0 = auto */
-	uint32_t reserved[2];
+	uint32_t force_threads;     /* threads per CTA of the scan kernel: 128..1024 (tuning); 0 = auto */
+	uint32_t force_stages;      /* ring depth of the per-warp TMA tile pipeline: 1..4 (tuning); 0 = auto */
+	uint32_t force_f2_bits;     /* log2 of the stage-2 bitmap size in bits, 13..19 (tuning); 0 = auto */
+	uint32_t force_r_bits;      /* log2 of the number of WM offset-mask entries, 10..16 (tuning); 0 = auto */
 } acwm_options;
 
 /* What the builder chose; for reports and tests. */
@@ -167,7 +168,8 @@ enum {
 	ACWM_BLOB_ENTRIES = 3,    /* acwm_ventry[] */
 	ACWM_BLOB_PATTERNS = 4,   /* distinct pattern bytes, back to back */
 	ACWM_BLOB_PARAMS = 5,     /* acwm_scan_params */
-	ACWM_BLOB_SYMCLASS = 6    /* bytes path AC: 256-entry symbol -> class map */
+	ACWM_BLOB_SYMCLASS = 6,   /* bytes path AC: 256-entry symbol -> class map */
+	ACWM_BLOB_RMASK = 7       /* WM, stride > 1: offset masks of the candidate blocks (uint8, uint16 for stride 16) */
 };
 int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_t *bytes);
 
@@ -191,7 +193,8 @@ typedef struct acwm_scan_params {
 	uint32_t hb_mult, hb_sh, n_buckets;           /* bucket = (key * mult) >> sh */
 	uint32_t n_entries;
 	uint32_t n_classes;     /* bytes path AC */
-	uint32_t reserved[8];
+	uint32_t r_mult, r_sh, r_entries, r_entry_bytes; /* WM offset masks: ridx = (block * mult) >> sh; 0 entries = none */
+	uint32_t reserved[4];
 } acwm_scan_params;
 
 /* ------------------- reference-shaped shims (smatcher.h) ------------------- */

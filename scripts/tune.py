@@ -18,9 +18,20 @@ torch.cuda.set_device(0)
 st = torch.cuda.current_stream().cuda_stream
 sizes = [int(x) for x in os.environ.get("TUNE_MIB", "128,1024").split(",")]
 wls = os.environ.get("TUNE_WL", "c2,c1,c2ac,c1wm").split(",")
-variants = {  # workload -> list of option dicts
-    "packed": [dict(force_threads=t, force_stages=st) for t in (512, 384, 256) for st in (2, 3)],
-    "bytes": [dict(force_threads=t, force_stages=st) for t in (512, 384, 256) for st in (2, 3)],
+def V(t, st, **kw):
+    d = dict(force_threads=t, force_stages=st)
+    d.update(kw)
+    return d
+
+variants = {  # workload -> list of option dicts ({} = what the builder picks)
+    "c2": [{}, V(1024, 1, force_f2_bits=17, force_r_bits=14), V(1024, 1, force_f2_bits=16, force_r_bits=14),
+           V(768, 1), V(768, 1, force_f2_bits=17, force_r_bits=14), V(512, 2), V(512, 1),
+           V(768, 1, force_stride=4), V(1024, 1, force_stride=4, force_f2_bits=16)],
+    "c1": [{}, V(1024, 1), V(768, 1), V(512, 2), V(512, 1), V(768, 1, force_stride=2)],
+    "c2ac": [{}, V(512, 1), V(256, 2)],
+    "c1wm": [{}, V(768, 1), V(512, 2)],
+    "c3wm": [{}],
+    "c4": [{}, V(512, 2), V(384, 2), V(384, 3)],
 }
 log("workload,text_mib,opts,stride,depth,exact,threads,smem,scan_us,finalize_us,GBps,frac_measured,count")
 texts = {}
@@ -29,12 +40,6 @@ for wl in wls:
     algo = acwm.AC if algo_name == "AC" else acwm.WM
     text0 = dg.text_host(128 << 20, alphabet, bench.TEXT_SEED)
     pats, m_max = bench.make_patterns(dg, text0, wl)
-    extra = []
-    if wl == "c1":
-        extra = [dict(force_stride=2), dict(force_threads=256, force_stages=4)]
-    if wl == "c2":
-        extra = [dict(force_stride=4), dict(force_stride=16)]
-    family = "packed" if alphabet <= 4 else "bytes"
     for mib in sizes:
         key = (alphabet, mib)
         if key not in texts:
@@ -43,7 +48,7 @@ for wl in wls:
             texts[key] = [dg.text_device(mib << 20, alphabet, 100 + k) for k in range(nrot)]
             texts[key][0][: 128 << 20].copy_(torch.from_numpy(text0)[: min(mib, 128) << 20])
         bufs = texts[key]
-        for opts in variants[family] + extra:
+        for opts in variants[wl]:
             try:
                 mt = acwm.Matcher(algo, pats, alphabet, **opts)
             except acwm.AcwmError as e:

@@ -34,6 +34,8 @@ class Emulator:
         self.bstart = mt.blob(acwm.BLOB_BUCKET_START).view(np.uint32)
         self.entries = mt.blob(acwm.BLOB_ENTRIES).view(acwm.VENTRY_DTYPE)
         self.pbytes = mt.blob(acwm.BLOB_PATTERNS)
+        rm = mt.blob(acwm.BLOB_RMASK)
+        self.rmask = rm.view(np.uint16 if self.p.r_entry_bytes == 2 else np.uint8) if rm.size else None
         self.info = mt.info
 
     # ------------------------------------------------------------ windows
@@ -124,6 +126,18 @@ class Emulator:
             return np.zeros(0, np.int64)
         return np.sort(np.concatenate(hits))
 
+    def _expand(self, cand, blocks, s, n):
+        """Candidate sample positions -> end positions to probe: the offsets r < s whose bit is set in
+        the offset mask of the candidate's block (probe_mask of FrontWM / FrontWMB)."""
+        if s == 1 or self.rmask is None:
+            ends = cand
+        else:
+            ri = (_mul32(blocks, self.p.r_mult) >> np.uint64(self.p.r_sh)).astype(np.int64)
+            masks = self.rmask[ri].astype(np.int64)
+            sel = (masks[:, None] >> np.arange(s)[None, :]) & 1
+            ends = (cand[:, None] + np.arange(s)[None, :])[sel == 1]
+        return ends[ends < n]
+
     def search(self, text):
         """-> (count, positions) exactly as the kernels would produce them."""
         p = self.p
@@ -151,9 +165,7 @@ class Emulator:
                 idx = _mul32(v >> np.uint64(p.f1_sh1), p.f1_mult) >> np.uint64(p.f1_sh2)
                 bm = self.front.view(np.uint32)
                 bit = (bm[(idx >> np.uint64(5)).astype(np.int64)] >> (idx & np.uint64(31)).astype(np.uint32)) & 1
-                cand = cpos[bit == 1]
-                ends = (cand[:, None] + np.arange(s)[None, :]).reshape(-1)
-                ends = ends[ends < n]
+                ends = self._expand(cpos[bit == 1], (v >> np.uint64(p.f1_sh1))[bit == 1], s, n)
             keys = win[ends] >> np.uint64(32 - 2 * p.b2)
         else:
             win = self._win8(text)
@@ -173,9 +185,7 @@ class Emulator:
                 idx = _mul32(_mix64(blk), p.f1_mult) >> np.uint64(p.f1_sh2)
                 bm = self.front.view(np.uint32)
                 bit = (bm[(idx >> np.uint64(5)).astype(np.int64)] >> (idx & np.uint64(31)).astype(np.uint32)) & 1
-                cand = cpos[bit == 1]
-                ends = (cand[:, None] + np.arange(s)[None, :]).reshape(-1)
-                ends = ends[ends < n]
+                ends = self._expand(cpos[bit == 1], _mix64(blk)[bit == 1], s, n)
             keys = _mix64(win[ends] >> np.uint64(64 - 8 * p.b2))
         res = self._verify(text, ends, keys)
         pos = []

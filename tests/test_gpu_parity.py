@@ -66,7 +66,8 @@ def test_empty_text(acwm, torch_cuda):
     assert count == 0 and pos.size == 0
 
 
-@pytest.mark.parametrize("threads,stages", [(128, 2), (256, 3), (384, 2), (512, 2), (256, 4), (384, 3)])
+@pytest.mark.parametrize("threads,stages", [(128, 2), (256, 3), (384, 2), (512, 2), (256, 4), (768, 1), (1024, 1),
+                                            (512, 1)])
 def test_launch_shape_variants(acwm, oracle, torch_cuda, threads, stages):
     """Every (warps, ring depth) shape of the scan kernel gives the same matches."""
     for cname in ("c1_ac_dna_p100_m8", "c2_wm_dna_p1000_m16", "ac_dna_depth5", "wm_ascii_p1000_m8",
@@ -74,6 +75,8 @@ def test_launch_shape_variants(acwm, oracle, torch_cuda, threads, stages):
         case = next(c for c in RANDOM_CASES if c[0] == cname)
         name, algo, alphabet, p, m, n, opts = case
         pats, text = make_case(case)
+        if alphabet > 4 and (stages < 2 or threads > 512):
+            continue  # the bytes path reads the raw tile while it walks: >= 2 slots, <= 16 warps
         _check(acwm, oracle, algo, pats, alphabet, text, force_threads=threads, force_stages=stages, **opts).close()
 
 
