@@ -77,6 +77,11 @@ def test_launch_shape_variants(acwm, oracle, torch_cuda, threads, stages):
         pats, text = make_case(case)
         if alphabet > 4 and (stages < 2 or threads > 512):
             continue  # the bytes path reads the raw tile while it walks: >= 2 slots, <= 16 warps
+        try:
+            acwm.Matcher(algo, pats, alphabet, force_threads=threads, force_stages=stages, **opts).close()
+        except acwm.AcwmError as e:
+            assert e.code == acwm.ERR_INVALID  # this shape does not fit next to the case's tables
+            continue
         _check(acwm, oracle, algo, pats, alphabet, text, force_threads=threads, force_stages=stages, **opts).close()
 
 
