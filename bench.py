@@ -236,6 +236,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    mt.set_overlap(not args.no_overlap)  # consecutive scans: programmatic dependent launches
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -258,6 +259,7 @@ def run_ours(args):
     text_bytes = sum(int(dev_texts[(args.warmup + i) % N_ROTATE].numel()) for i in range(args.steps)) / args.steps
     value = world * text_bytes / (ms_per_step * 1e-3) / 1e9
 
+    mt.set_overlap(False)
     # ---- results of the last step (parity of the global count is a test, here it is reported)
     last_count, last_pos, _ = mt.fetch(cap=pos_cap, stream=stream)
     global_count = sh.allreduce_count(last_count, dev)
@@ -328,6 +330,8 @@ def run_ours(args):
                        "text_bytes_per_gpu": n, "halo_bytes": halo,
                        "l2": f"{N_ROTATE} distinct {args.text_mib} MiB texts cycled (working set > L2)",
                        "positions": "count + sorted uint64 positions produced every step",
+                       "launch": "one cooperative kernel per step" + ("" if args.no_overlap else
+                                 ", consecutive steps chained as programmatic dependent launches"),
                        "kernel": {k: info[k] for k in ("packed2bit", "stride", "depth", "exact_front", "n_rows",
                                                         "table_in_smem", "smem_bytes", "threads", "stages")}},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": e2e_bytes,
@@ -398,6 +402,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--text-mib", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="plain stream-ordered launches in the timed loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

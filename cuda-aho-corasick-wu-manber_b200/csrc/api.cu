@@ -137,7 +137,7 @@ static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
 // Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
 // cooperative kernel that scans, orders the positions and publishes the result block.
 static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
-		uint64_t tile_hi, int want_positions, int append, cudaStream_t st) {
+		uint64_t tile_hi, int want_positions, int append, int overlap, cudaStream_t st) {
 	const Compiled &c = mt->c;
 	ScanArgs a;
 	memset(&a, 0, sizeof(a));
@@ -165,17 +165,22 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.tile_count = mt->d_tile_count;
 	a.cta_total = mt->d_cta_total;
 	a.stages = c.info.stages;
+	a.epoch = mt->epoch++;
+	a.overlap = overlap;
 	a.want_positions = want_positions;
 	a.append = append;
 	const uint32_t threads = c.info.threads, warps = threads / 32;
 	const uint64_t ntl = tile_hi - tile_lo;
 	// every CTA owns a contiguous span of whole "rounds" (one tile per warp)
-	uint32_t grid = (uint32_t) std::min<uint64_t>((uint64_t) mt->sm_count, (ntl + warps - 1) / warps);
+	uint32_t grid = (uint32_t) std::min<uint64_t>((uint64_t) std::min(mt->sm_count, 256), (ntl + warps - 1) / warps);
 	grid = std::max(grid, 1u);
 	a.tiles_per_cta = std::max<uint64_t>(1, (ntl + grid - 1) / grid);
 	grid = (uint32_t) std::max<uint64_t>(1, (ntl + a.tiles_per_cta - 1) / a.tiles_per_cta);
-	cudaError_t e = c.prm.packed2bit ? launch_scan_packed(a, threads, c.info.smem_bytes, grid, st)
-									 : launch_scan_bytes(a, threads, c.info.smem_bytes, grid, st);
+	// per-tile counts of a span stay in whatever shared memory the tables and the rings leave free
+	a.cnt_cap = (uint32_t) std::min<uint64_t>(a.tiles_per_cta, (kMaxSmem - c.info.smem_bytes) / 4);
+	const uint32_t smem = c.info.smem_bytes + a.cnt_cap * 4;
+	cudaError_t e = c.prm.packed2bit ? launch_scan_packed(a, threads, smem, grid, st)
+									 : launch_scan_bytes(a, threads, smem, grid, st);
 	if (e != cudaSuccess)
 		return cuda_fail(e, "scan kernel launch");
 	mt->launches++;
@@ -246,7 +251,7 @@ int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64
 				CU(cudaEventCreate(&e));
 		CU(cudaEventRecord(mt->ev_prof[0], st));
 	}
-	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, 0, st)))
+	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, 0, mt->overlap, st)))
 		return rc;
 	if (mt->profiling)
 		CU(cudaEventRecord(mt->ev_prof[1], st));
@@ -334,7 +339,7 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
 		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
 		if ((rc = launch_scan(mt, mt->d_text, n, 0, std::min(n_tiles, ci * chunk_tiles),
-					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, mt->s_scan)))
+					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, 0, mt->s_scan)))
 			return rc;
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
 	}
@@ -351,6 +356,13 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 }
 
 double acwm_last_kernel_seconds(const acwm_matcher *mt) { return mt ? mt->last_kernel_s : 0.0; }
+
+int acwm_set_overlap(acwm_matcher *mt, int on) {
+	if (!mt)
+		return set_error(ACWM_ERR_INVALID, "matcher == NULL");
+	mt->overlap = on != 0;
+	return ACWM_OK;
+}
 
 int acwm_set_profiling(acwm_matcher *mt, int on) {
 	if (!mt)

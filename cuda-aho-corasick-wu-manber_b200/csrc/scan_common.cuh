@@ -16,20 +16,20 @@ struct Result {
 	unsigned int overflow;       // more matches than position capacity
 };
 
-// Working counters of the launch in flight.  All zero between launches: the last CTA
-// of every launch folds them into `result` and clears them, so no memset is needed.
+// Working counters of the launch in flight.  Two copies: launch k uses work[k & 1] and
+// clears work[(k + 1) & 1] for its successor (which starts only after k is done), so no
+// memset node is needed between scans.
 struct Work {
-	unsigned long long count;
+	unsigned long long arrive;   // [CTAs arrived : 16 | matches : 48] -- one atomic per CTA is count, grid barrier and exit ticket
 	unsigned long long cursor;   // staging slots handed out
 	unsigned int bad_text;
-	unsigned int arrived;        // grid barrier
-	unsigned int done;           // exit ticket
-	unsigned int pad;
+	unsigned int pad[3];
 };
+constexpr unsigned kArriveShift = 48;
 
 struct Control {
 	Result result;
-	Work work;
+	Work work[2];
 };
 
 struct ScanArgs {
@@ -55,6 +55,9 @@ struct ScanArgs {
 	uint32_t *tile_count;        // matches per tile -> (in the epilogue) exclusive prefix within the owning CTA
 	unsigned long long *cta_total; // matches per CTA
 	uint32_t stages;             // ring depth of the per-warp tile pipeline
+	uint32_t cnt_cap;            // per-tile counts of the first cnt_cap tiles of a span live in shared memory
+	uint32_t epoch;              // launch number of this matcher: selects the Work copy
+	int overlap;                 // 1: the caller allows this scan to start while the previous kernel of the stream drains
 	int want_positions;
 	int append;                  // 1: add to ctl->result instead of replacing it (chunked host text)
 };
@@ -125,30 +128,25 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 			: "memory");
 }
 
-// ------------------------------------------------------------ grid barrier (cooperative launch: all CTAs resident)
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
-	unsigned int v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// ------------------------------------------------------------ grid-wide arrival (cooperative launch: all CTAs resident)
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ void grid_barrier(unsigned int *arrived) {
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		atomicAdd(arrived, 1u);
-		while (ld_acquire_u32(arrived) < gridDim.x)
-			__nanosleep(64);
-		__threadfence();
-	}
-	__syncthreads();
-}
+// programmatic dependent launch: wait for the previous kernel of the stream / let the next one start
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Warp-level staging of the matches of one tile.  A warp reserves staging slots in blocks
 // (one atomic per >= kStageBlock matches instead of one per tile) and leaves the unused
 // tail of its last block marked with all-ones.
 struct Emitter {
 	const ScanArgs *a;
+	Work *wk;
+	uint32_t *s_cnt;             // shared-memory per-tile counts (first a->cnt_cap tiles of the span)
 	uint64_t tile;
+	uint32_t idx;                // span-relative index of the tile
 	unsigned long long warp_count;
 	unsigned long long blk_ptr, old_ptr, new_ptr;
 	uint32_t blk_left, old_left;
@@ -163,7 +161,7 @@ struct Emitter {
 			const uint32_t grab = max(extra, kStageBlock);
 			unsigned long long p = 0;
 			if (lane_id() == 0)
-				p = atomicAdd(&a->ctl->work.cursor, (unsigned long long) grab);
+				p = atomicAdd(&wk->cursor, (unsigned long long) grab);
 			new_ptr = __shfl_sync(kFull, p, 0);
 			blk_ptr = new_ptr + extra;
 			blk_left = grab - extra;
@@ -179,8 +177,12 @@ struct Emitter {
 			a->staging[slot] = encode_stage(tile, k, pos);
 	}
 	__device__ __forceinline__ void end_tile(uint32_t total) {
-		if (a->want_positions && lane_id() == 0)
-			a->tile_count[tile] = total;
+		if (a->want_positions && lane_id() == 0) {
+			if (idx < a->cnt_cap)
+				s_cnt[idx] = total;
+			else
+				a->tile_count[tile] = total;
+		}
 		warp_count += total;
 	}
 	__device__ __forceinline__ void finish() const {

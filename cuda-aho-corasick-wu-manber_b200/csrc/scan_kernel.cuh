@@ -11,8 +11,12 @@
 //   2. order    the CTA turns the per-tile counts of its span into exclusive offsets, all
 //               CTAs meet at one grid barrier, every CTA derives the span bases from the
 //               per-CTA totals and the staged matches drop into their sorted slots;
-//   3. publish  the last CTA out folds the working counters into the result block and
-//               clears them for the next launch (no memset node between scans).
+//   3. publish  the arrival at the grid barrier is ONE 64-bit atomic per CTA that also carries
+//               the CTA's match count; the last CTA to arrive writes the result block.  The
+//               working counters are double-buffered by launch parity, each launch clears its
+//               successor's copy (no memset node between scans).
+// With `overlap` the launch is a programmatic dependent launch: its prologue and its first
+// tile loads run while the previous scan of the stream drains (griddepcontrol).
 #pragma once
 #include "scan_common.cuh"
 
@@ -52,6 +56,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	// [CTA scratch 1 KiB][front table][offset masks][stage-2 bitmap][per-warp areas]
 	uint64_t *tab_bar = reinterpret_cast<uint64_t *>(smem);
 	uint32_t *s_next = reinterpret_cast<uint32_t *>(smem + 16); // next unclaimed tile of this CTA's span
+	uint32_t *s_bad = reinterpret_cast<uint32_t *>(smem + 20);
+	unsigned long long *s_count = reinterpret_cast<unsigned long long *>(smem + 24); // matches of this CTA
+	unsigned long long *s_misc = reinterpret_cast<unsigned long long *>(smem + 32);  // [0] cursor, [1] append base
 	uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + 64); // 33 words
 	const uint32_t front_smem = a.front_in_smem ? ((a.front_bytes + 15u) & ~15u) : 0u;
 	const uint32_t rm_bytes = EXACT ? 0u : ((a.prm.r_entries * a.prm.r_entry_bytes + 15u) & ~15u);
@@ -68,10 +75,15 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + stages * kBufBytes);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + stages * kBufBytes + (kPacked ? kPackWords * 4 : 0));
 	uint32_t *s_tid = reinterpret_cast<uint32_t *>(bars + kMaxStages); // span-relative tile index per ring slot
+	uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_warps + W * warp_smem_bytes(stages, kPacked)); // a.cnt_cap words
 
+	if (!a.overlap)
+		pdl_wait(); // everything the previous kernel of the stream wrote (possibly our text) is visible from here
 	if (threadIdx.x == 0) {
 		mbar_init(tab_bar, 1);
 		*s_next = 0;
+		*s_bad = 0;
+		*s_count = 0;
 	}
 	if (lane == 0)
 		for (uint32_t s = 0; s < stages; s++)
@@ -137,8 +149,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	__syncwarp();
 
 	uint32_t badacc = 0;
+	Work *wk = &a.ctl->work[a.epoch & 1u];
 	Emitter em;
 	em.a = &a;
+	em.wk = wk;
+	em.s_cnt = s_cnt;
+	em.idx = 0;
 	em.tile = 0;
 	em.warp_count = 0;
 	em.blk_ptr = em.old_ptr = em.new_ptr = 0;
@@ -148,6 +164,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		mbar_wait(tab_bar, 0);
 	fr.init(s_front, s_rmask, a);
 
+	bool waited = false;
 	for (uint32_t slot = 0;; slot = slot + 1 == stages ? 0 : slot + 1) {
 		const uint32_t idx = s_tid[slot];
 		if (idx >= n_b)
@@ -166,8 +183,13 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			refill(slot);
 		}
 		fr.walk(a);
+		if (a.overlap && !waited) { // nothing has been written to global memory so far
+			pdl_wait();
+			waited = true;
+		}
 
 		em.tile = tile;
+		em.idx = idx;
 		const uint64_t tile_start = tile * (uint64_t) kTile;
 		uint32_t total = 0;
 		if constexpr (EXACT) {
@@ -271,26 +293,30 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		if constexpr (!kPacked)
 			refill(slot);
 	}
+	if (a.overlap && !waited)
+		pdl_wait();
+	pdl_trigger(); // the next scan of the stream may start its prologue as our CTAs retire
 	em.finish();
 
-	// ---- per-warp totals
-	Work *wk = &a.ctl->work;
+	// ---- per-CTA totals (shared memory)
 	if (lane == 0 && em.warp_count)
-		atomicAdd(&wk->count, em.warp_count);
+		atomicAdd(s_count, em.warp_count);
 	if constexpr (kPacked) {
 		badacc &= 0xFCFCFCFCu;
 		if (__any_sync(kFull, badacc != 0) && lane == 0)
-			atomicOr(&wk->bad_text, 1u);
+			atomicOr(s_bad, 1u);
 	}
+	__syncthreads();
 
-	// ---- order: staged matches -> sorted positions
+	// ---- order, part 1: exclusive prefix of the per-tile counts inside this CTA's span
+	const uint32_t G = gridDim.x;
 	if (a.want_positions) {
-		__syncthreads();
-		// exclusive prefix of the per-tile counts inside this CTA's span (in place)
 		uint32_t carry = 0;
 		for (uint32_t base = 0; base < n_b; base += THREADS) {
 			const uint32_t i = base + threadIdx.x;
-			const uint32_t v = i < n_b ? __ldcg(a.tile_count + cta_lo + i) : 0u;
+			uint32_t v = 0;
+			if (i < n_b)
+				v = i < a.cnt_cap ? s_cnt[i] : __ldcg(a.tile_count + cta_lo + i);
 			const uint32_t incl = warp_incl_scan(v);
 			if (lane == 31)
 				s_scan[warp] = incl;
@@ -310,82 +336,103 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		}
 		if (threadIdx.x == 0)
 			a.cta_total[blockIdx.x] = carry;
-
-		grid_barrier(&wk->arrived);
-
-		// span bases: exclusive prefix of the per-CTA totals (the ring buffers are free now)
-		unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_warps);
-		if (warp == 0) {
-			unsigned long long run = a.append ? __ldcg(&a.ctl->result.written) : 0ull;
-			for (uint32_t b0 = 0; b0 < gridDim.x; b0 += 32) {
-				const uint32_t b = b0 + lane;
-				const unsigned long long v = b < gridDim.x ? __ldcg(a.cta_total + b) : 0ull;
-				unsigned long long incl = v;
-#pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					const unsigned long long t = __shfl_up_sync(kFull, incl, d);
-					if ((int) lane >= d)
-						incl += t;
-				}
-				if (b < gridDim.x)
-					s_base[b] = run + incl - v;
-				run += __shfl_sync(kFull, incl, 31);
-			}
-		}
 		__syncthreads();
-		const unsigned long long cursor = __ldcg(&wk->cursor);
-		const uint64_t staged = cursor < a.stage_cap ? cursor : a.stage_cap;
-		const uint64_t stride = (uint64_t) gridDim.x * THREADS;
-		for (uint64_t i = (uint64_t) blockIdx.x * THREADS + threadIdx.x; i < staged; i += stride) {
-			const uint64_t e = __ldcg(a.staging + i);
-			if (e == ~0ull)
-				continue; // unused tail of a warp's reservation
-			const uint64_t tile = e >> (kRankBits + kPosBits);
-			const uint32_t rank = (uint32_t) (e >> kPosBits) & ((1u << kRankBits) - 1);
-			const uint32_t pos = (uint32_t) e & ((1u << kPosBits) - 1);
-			const uint64_t owner = (tile - a.tile_lo) / a.tiles_per_cta;
-			const uint64_t at = s_base[owner] + __ldcg(a.tile_count + tile) + rank;
-			if (at < a.cap)
-				a.positions[at] = tile * kTile + pos - a.data_lo;
-		}
 	}
 
-	// ---- publish: the last CTA out folds the working counters into the result and clears them
-	__syncthreads();
+	// ---- arrive: count + grid barrier + exit ticket in one atomic; the last CTA publishes
 	if (threadIdx.x == 0) {
+		Work *other = &a.ctl->work[(a.epoch + 1u) & 1u];
+		if (blockIdx.x == 0) { // the successor launch's counters (its predecessor -- us -- is the only one that could still use them)
+			other->arrive = 0;
+			other->cursor = 0;
+			other->bad_text = 0;
+		}
+		Result *res = &a.ctl->result;
+		unsigned long long old_count = 0, old_written = 0;
+		unsigned int old_bad = 0, old_ovf = 0;
+		if (a.append) { // read before anybody can publish (nobody publishes before we have arrived)
+			old_count = __ldcg(&res->count);
+			old_written = __ldcg(&res->written);
+			old_bad = __ldcg(&res->bad_text);
+			old_ovf = __ldcg(&res->overflow);
+		}
+		s_misc[1] = old_written;
+		if (*s_bad)
+			atomicOr(&wk->bad_text, 1u);
 		__threadfence();
-		const unsigned int ticket = atomicAdd(&wk->done, 1u);
-		if (ticket == gridDim.x - 1) {
+		const unsigned long long mine = *s_count;
+		const unsigned long long before = atomicAdd(&wk->arrive, (1ull << kArriveShift) + mine);
+		if ((before >> kArriveShift) == G - 1) { // everybody has arrived: totals are final
 			__threadfence();
-			Result *res = &a.ctl->result;
-			const unsigned long long cnt = __ldcg(&wk->count), cur = __ldcg(&wk->cursor);
-			const unsigned int bad = __ldcg(&wk->bad_text);
-			unsigned long long r_count = 0, r_written = 0;
-			unsigned int r_bad = 0, r_ovf = 0;
-			if (a.append) {
-				r_count = res->count;
-				r_written = res->written;
-				r_bad = res->bad_text;
-				r_ovf = res->overflow;
-			}
-			r_count += cnt;
+			const unsigned long long cnt = (before & ((1ull << kArriveShift) - 1)) + mine;
+			const unsigned long long cur = __ldcg(&wk->cursor);
+			unsigned long long r_written = old_written;
+			unsigned int r_ovf = old_ovf;
 			if (a.want_positions) {
-				if (r_written + cnt > a.cap || cur > a.stage_cap) {
+				if (old_written + cnt > a.cap || cur > a.stage_cap) {
 					r_ovf = 1;
-					r_written = min(r_written + cnt, (unsigned long long) a.cap);
+					r_written = min(old_written + cnt, (unsigned long long) a.cap);
 				} else
 					r_written += cnt;
 			}
-			res->count = r_count;
+			res->count = old_count + cnt;
 			res->written = r_written;
-			res->bad_text = r_bad | bad;
+			res->bad_text = old_bad | __ldcg(&wk->bad_text);
 			res->overflow = r_ovf;
-			wk->count = 0;
-			wk->cursor = 0;
-			wk->bad_text = 0;
-			wk->arrived = 0;
-			wk->done = 0;
 		}
+		if (a.want_positions) {
+			while ((ld_acquire_u64(&wk->arrive) >> kArriveShift) < G)
+				__nanosleep(32);
+			__threadfence();
+		}
+	}
+	if (!a.want_positions)
+		return;
+	__syncthreads();
+
+	// ---- order, part 2: span bases = exclusive prefix of the per-CTA totals, then the scatter
+	unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_warps); // the ring buffers are free now
+	if (warp == 0) {
+		constexpr uint32_t kMaxChunks = 8; // grids of up to 256 CTAs in one batch of loads
+		unsigned long long v[kMaxChunks];
+#pragma unroll
+		for (uint32_t c = 0; c < kMaxChunks; c++) {
+			const uint32_t b = c * 32 + lane;
+			v[c] = b < G ? __ldcg(a.cta_total + b) : 0ull;
+		}
+		if (lane == 0)
+			s_misc[0] = __ldcg(&wk->cursor);
+		unsigned long long run = s_misc[1];
+#pragma unroll
+		for (uint32_t c = 0; c < kMaxChunks; c++) {
+			unsigned long long incl = v[c];
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const unsigned long long t = __shfl_up_sync(kFull, incl, d);
+				if ((int) lane >= d)
+					incl += t;
+			}
+			const uint32_t b = c * 32 + lane;
+			if (b < G)
+				s_base[b] = run + incl - v[c];
+			run += __shfl_sync(kFull, incl, 31);
+		}
+	}
+	__syncthreads();
+	const unsigned long long cursor = s_misc[0];
+	const uint64_t staged = cursor < a.stage_cap ? cursor : a.stage_cap;
+	const uint64_t stride = (uint64_t) G * THREADS;
+	for (uint64_t i = (uint64_t) blockIdx.x * THREADS + threadIdx.x; i < staged; i += stride) {
+		const uint64_t e = __ldcg(a.staging + i);
+		if (e == ~0ull)
+			continue; // unused tail of a warp's reservation
+		const uint64_t tile = e >> (kRankBits + kPosBits);
+		const uint32_t rank = (uint32_t) (e >> kPosBits) & ((1u << kRankBits) - 1);
+		const uint32_t pos = (uint32_t) e & ((1u << kPosBits) - 1);
+		const uint64_t owner = (tile - a.tile_lo) / a.tiles_per_cta;
+		const uint64_t at = s_base[owner] + __ldcg(a.tile_count + tile) + rank;
+		if (at < a.cap)
+			a.positions[at] = tile * kTile + pos - a.data_lo;
 	}
 }
 
@@ -393,20 +440,31 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 template <class Front, bool EXACT, int THREADS>
 static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid, cudaStream_t st) {
 	auto kern = scan_kernel<Front, EXACT, THREADS>;
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	static bool attr_set[64] = {};
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess)
 		return e;
+	if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+		e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxSmem);
+		if (e != cudaSuccess)
+			return e;
+		if (dev >= 0 && dev < 64)
+			attr_set[dev] = true;
+	}
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.gridDim = dim3(grid);
 	cfg.blockDim = dim3(THREADS);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = st;
-	cudaLaunchAttribute attr[1];
+	cudaLaunchAttribute attr[2];
 	attr[0].id = cudaLaunchAttributeCooperative; // the grid barrier needs every CTA resident
 	attr[0].val.cooperative = 1;
+	attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[1].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
-	cfg.numAttrs = 1;
+	cfg.numAttrs = a.overlap ? 2 : 1;
 	return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
