@@ -87,7 +87,6 @@ def lib():
         L.acwm_last_kernel_seconds.restype = C.c_double
         L.acwm_last_kernel_seconds.argtypes = [C.c_void_p]
         L.acwm_set_profiling.argtypes = [C.c_void_p, C.c_int]
-        L.acwm_set_overlap.argtypes = [C.c_void_p, C.c_int]
         L.acwm_profiled_seconds.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.acwm_launch_count.restype = C.c_ulonglong
         L.acwm_launch_count.argtypes = [C.c_void_p]
@@ -220,10 +219,6 @@ class Matcher:
                     allow=(ERR_OVERFLOW,) if allow_overflow else ())
         self.last_rc = rc
         return int(count.value), pos[:int(nw.value)]
-
-    def set_overlap(self, on: bool):
-        """Back-to-back scans on one stream may overlap (programmatic dependent launch); see acwm.h."""
-        _check(lib().acwm_set_overlap(self._h, int(on)))
 
     def set_profiling(self, on: bool):
         _check(lib().acwm_set_profiling(self._h, int(on)))

@@ -137,7 +137,7 @@ static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
 // Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
 // cooperative kernel that scans, orders the positions and publishes the result block.
 static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
-		uint64_t tile_hi, int want_positions, int append, int overlap, cudaStream_t st) {
+		uint64_t tile_hi, int want_positions, int append, cudaStream_t st) {
 	const Compiled &c = mt->c;
 	ScanArgs a;
 	memset(&a, 0, sizeof(a));
@@ -166,7 +166,6 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.cta_total = mt->d_cta_total;
 	a.stages = c.info.stages;
 	a.epoch = mt->epoch++;
-	a.overlap = overlap;
 	a.want_positions = want_positions;
 	a.append = append;
 	const uint32_t threads = c.info.threads, warps = threads / 32;
@@ -251,7 +250,7 @@ int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64
 				CU(cudaEventCreate(&e));
 		CU(cudaEventRecord(mt->ev_prof[0], st));
 	}
-	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, 0, mt->overlap, st)))
+	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, 0, st)))
 		return rc;
 	if (mt->profiling)
 		CU(cudaEventRecord(mt->ev_prof[1], st));
@@ -339,7 +338,7 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
 		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
 		if ((rc = launch_scan(mt, mt->d_text, n, 0, std::min(n_tiles, ci * chunk_tiles),
-					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, 0, mt->s_scan)))
+					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, mt->s_scan)))
 			return rc;
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
 	}
@@ -356,13 +355,6 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 }
 
 double acwm_last_kernel_seconds(const acwm_matcher *mt) { return mt ? mt->last_kernel_s : 0.0; }
-
-int acwm_set_overlap(acwm_matcher *mt, int on) {
-	if (!mt)
-		return set_error(ACWM_ERR_INVALID, "matcher == NULL");
-	mt->overlap = on != 0;
-	return ACWM_OK;
-}
 
 int acwm_set_profiling(acwm_matcher *mt, int on) {
 	if (!mt)

@@ -47,7 +47,6 @@ struct acwm_matcher {
 	std::vector<cudaEvent_t> ev_time;
 	std::array<cudaEvent_t, 2> ev_prof{};
 	bool profiling = false;
-	int overlap = 0;
 	uint32_t epoch = 0;
 	double last_kernel_s = 0;
 	int last_want_positions = 0;

@@ -57,7 +57,6 @@ struct ScanArgs {
 	uint32_t stages;             // ring depth of the per-warp tile pipeline
 	uint32_t cnt_cap;            // per-tile counts of the first cnt_cap tiles of a span live in shared memory
 	uint32_t epoch;              // launch number of this matcher: selects the Work copy
-	int overlap;                 // 1: the caller allows this scan to start while the previous kernel of the stream drains
 	int want_positions;
 	int append;                  // 1: add to ctl->result instead of replacing it (chunked host text)
 };
@@ -134,9 +133,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
-// programmatic dependent launch: wait for the previous kernel of the stream / let the next one start
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Warp-level staging of the matches of one tile.  A warp reserves staging slots in blocks
 // (one atomic per >= kStageBlock matches instead of one per tile) and leaves the unused

@@ -15,8 +15,6 @@
 //               the CTA's match count; the last CTA to arrive writes the result block.  The
 //               working counters are double-buffered by launch parity, each launch clears its
 //               successor's copy (no memset node between scans).
-// With `overlap` the launch is a programmatic dependent launch: its prologue and its first
-// tile loads run while the previous scan of the stream drains (griddepcontrol).
 #pragma once
 #include "scan_common.cuh"
 
@@ -75,10 +73,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + stages * kBufBytes);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + stages * kBufBytes + (kPacked ? kPackWords * 4 : 0));
 	uint32_t *s_tid = reinterpret_cast<uint32_t *>(bars + kMaxStages); // span-relative tile index per ring slot
+	uint16_t *lst = reinterpret_cast<uint16_t *>(bars + 2 * kMaxStages);  // match positions of the current tile
 	uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_warps + W * warp_smem_bytes(stages, kPacked)); // a.cnt_cap words
 
-	if (!a.overlap)
-		pdl_wait(); // everything the previous kernel of the stream wrote (possibly our text) is visible from here
 	if (threadIdx.x == 0) {
 		mbar_init(tab_bar, 1);
 		*s_next = 0;
@@ -164,7 +161,6 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		mbar_wait(tab_bar, 0);
 	fr.init(s_front, s_rmask, a);
 
-	bool waited = false;
 	for (uint32_t slot = 0;; slot = slot + 1 == stages ? 0 : slot + 1) {
 		const uint32_t idx = s_tid[slot];
 		if (idx >= n_b)
@@ -183,10 +179,6 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			refill(slot);
 		}
 		fr.walk(a);
-		if (a.overlap && !waited) { // nothing has been written to global memory so far
-			pdl_wait();
-			waited = true;
-		}
 
 		em.tile = tile;
 		em.idx = idx;
@@ -208,14 +200,19 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 				if (a.want_positions) {
 					em.reserve(total);
 					uint32_t k = incl - cnt;
+					if (total <= kListCap) { // the usual case: positions -> shared list, then full-warp stores
 #pragma unroll
-					for (int g = 0; g < Front::kWords; g++) {
-						uint32_t w = fr.hw[g];
-						while (w) {
-							const int b = __ffs(w) - 1;
-							w &= w - 1;
-							em.put(k++, lane * kLane + Front::sym_of(g, b));
-						}
+						for (int g = 0; g < Front::kWords; g++)
+							for (uint32_t w = fr.hw[g]; w; w &= w - 1)
+								lst[k++] = (uint16_t) (lane * kLane + Front::sym_of(g, __ffs(w) - 1));
+						__syncwarp();
+						for (uint32_t i = lane; i < total; i += 32)
+							em.put(i, lst[i]);
+					} else {
+#pragma unroll
+						for (int g = 0; g < Front::kWords; g++)
+							for (uint32_t w = fr.hw[g]; w; w &= w - 1)
+								em.put(k++, lane * kLane + Front::sym_of(g, __ffs(w) - 1));
 					}
 				}
 			}
@@ -277,14 +274,24 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 				if (a.want_positions) {
 					em.reserve(total);
 					uint32_t k = incl - cnt;
+					const bool listed = total <= kListCap;
 #pragma unroll
 					for (int g = 0; g < 4; g++)
 						for (uint32_t w = mw[g]; w; w &= w - 1) {
 							const uint32_t p = 32 * g + __ffs(w) - 1;
 							const uint32_t reps = multi ? mult_at(p) : 1u;
-							for (uint32_t i = 0; i < reps; i++)
-								em.put(k++, lane * kLane + p);
+							for (uint32_t i = 0; i < reps; i++, k++) {
+								if (listed)
+									lst[k] = (uint16_t) (lane * kLane + p);
+								else
+									em.put(k, lane * kLane + p);
+							}
 						}
+					if (listed) {
+						__syncwarp();
+						for (uint32_t i = lane; i < total; i += 32)
+							em.put(i, lst[i]);
+					}
 				}
 			}
 		}
@@ -293,9 +300,6 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		if constexpr (!kPacked)
 			refill(slot);
 	}
-	if (a.overlap && !waited)
-		pdl_wait();
-	pdl_trigger(); // the next scan of the stream may start its prologue as our CTAs retire
 	em.finish();
 
 	// ---- per-CTA totals (shared memory)
@@ -458,13 +462,11 @@ static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid,
 	cfg.blockDim = dim3(THREADS);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = st;
-	cudaLaunchAttribute attr[2];
+	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeCooperative; // the grid barrier needs every CTA resident
 	attr[0].val.cooperative = 1;
-	attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[1].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
-	cfg.numAttrs = a.overlap ? 2 : 1;
+	cfg.numAttrs = 1;
 	return cudaLaunchKernelEx(&cfg, kern, a);
 }
 

@@ -5,7 +5,7 @@
 // registers, 16 symbols -> one 32-bit word (4 IMAD + 3 PRMT), so the walk below runs on
 // 8 registers per lane:
 //   AC<K>  dense DFA with the failure function folded in, K symbols per shared-memory
-//          lookup (uint16 entry = next_row << K | K hit bits).  Supersedes the
+//          lookup (uint16 entry = byte offset of the next row | K hit bits).  Supersedes the
 //          one-symbol goto/failure walk of cuda/cuda_ac.cu:88-95.
 //   WM<S>  Wu-Manber block filter sampled every S symbols (SHIFT[block] < S as a
 //          bitmap).  Supersedes the divergent skip loop of cuda/cuda_wm.cu:136-176.
@@ -80,7 +80,7 @@ struct FrontAC : PackedKey {
 	static constexpr int kExpand = 1; // probes per candidate
 
 	const uint8_t *tab; // shared-memory DFA
-	uint32_t ent;       // current entry (row << K | hits)
+	uint32_t ent;       // current entry (byte offset of the row | hits)
 	uint32_t nwu, hist; // warm-up strides / symbols of history they (and the first in-chunk stride) cover
 	uint32_t W[8];      // W[0] = the 16 symbols in front of the chunk, W[1..7] = the chunk
 	uint32_t H[3];      // long warm-up only: symbols -64..-17
@@ -100,7 +100,7 @@ struct FrontAC : PackedKey {
 	}
 
 	__device__ __forceinline__ uint32_t step(uint32_t sym2) {
-		const uint32_t addr = ((ent << (K + 1)) & kRowMask) | sym2;
+		const uint32_t addr = (ent & kRowMask) | sym2; // one LOP3 between two dependent lookups
 		ent = *reinterpret_cast<const uint16_t *>(tab + addr);
 		return ent & kHitMask;
 	}

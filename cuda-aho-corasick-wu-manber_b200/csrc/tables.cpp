@@ -105,8 +105,9 @@ static void build_verify(const PatternSet &ps, bool packed, const acwm_options &
 	prm.b2 = b2;
 	// stage-2 bitmap: direct index when the key space is small, hashed otherwise
 	const uint32_t key_bits = packed ? 2 * b2 : 32;
-	// ~0.4 % of the probes pass: a pass costs dependent L2 loads (buckets), so it has to be rare
-	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 256), 13), 18);
+	// ~1.5 % of the probes pass (a pass costs dependent L2 loads in the buckets); a larger bitmap
+	// measured no faster (profiles/r01d_tune.csv) and every CTA has to load it
+	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 64), 13), 18);
 	if (opts.force_f2_bits)
 		f2bits = std::min<uint32_t>(std::max<uint32_t>(opts.force_f2_bits, 13), 19);
 	if (packed && key_bits <= f2bits) {
@@ -266,7 +267,8 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 	if (opts.force_depth) {
 		d_lo = d_hi = std::min<uint32_t>(std::max<uint32_t>(opts.force_depth, 1), Dmax);
 	}
-	const uint32_t max_rows_any = std::min<uint32_t>(budget / 8, (1u << 15) - 1); // K = 1
+	// entry = byte offset of the next row | hit bits, 16 bits: rows * row_bytes < 65536
+	const uint32_t max_rows_any = std::min<uint32_t>(budget / 8, (1u << 13) - 1); // K = 1
 	for (uint32_t D = d_hi; D >= d_lo; D--) {
 		Trie t;
 		build_suffix_trie(ps, D, 4, nullptr, max_rows_any, t);
@@ -278,7 +280,7 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 			if (opts.force_stride && opts.force_stride != K)
 				continue;
 			const uint64_t bytes = (uint64_t) t.rows << (2 * K + 1);
-			if (bytes > budget || t.rows >= (1u << (16 - K)))
+			if (bytes > budget || bytes >= 65536)
 				continue;
 			const double cost = 7.0 / K + rate * 25.0;
 			if (cost < best_cost - 1e-9) {
@@ -309,7 +311,7 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 				hits |= (e & 1) << i;
 				st = e >> 1;
 			}
-			tab[(size_t) r * cols + idx] = (uint16_t) ((st << K) | hits);
+			tab[(size_t) r * cols + idx] = (uint16_t) ((st << (2 * K + 1)) | hits);
 		}
 	prm.stride = K;
 	prm.depth = bestD;
@@ -463,7 +465,7 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 	memcpy(c.front.data(), bm.data(), c.front.size());
 	// offset masks: a candidate block only has to be probed at the offsets r some pattern holds it at
 	if (s > 1) {
-		uint32_t rbits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 4), 10), 15);
+		uint32_t rbits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 2), 10), 15);
 		if (opts.force_r_bits)
 			rbits = std::min<uint32_t>(std::max<uint32_t>(opts.force_r_bits, 10), 16);
 		prm.r_mult = kMultR;

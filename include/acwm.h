@@ -137,13 +137,6 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
  * its kernels: cuda/cuda_wm.cu:264-289) of the last acwm_search_host call. */
 double acwm_last_kernel_seconds(const acwm_matcher *mt);
 
-/* Back-to-back scans: with overlap on, acwm_scan_device launches its kernel as a programmatic
- * dependent launch, so its prologue (table and first tile loads) runs while the previous
- * kernel of the stream drains.  The caller guarantees that the text is NOT produced by the
- * kernel that immediately precedes the scan on that stream (an earlier scan of this matcher,
- * a copy or an event wait are fine).  Off by default. */
-int acwm_set_overlap(acwm_matcher *mt, int on);
-
 /* Bench instrumentation: with profiling on, acwm_scan_device brackets the scan kernel and
  * the finalize kernels with CUDA events on the caller's stream; acwm_profiled_seconds
  * waits for the last profiled scan and returns the two durations. */

@@ -84,7 +84,7 @@ class Emulator:
         return out
 
     # ------------------------------------------------------------ front ends
-    def _ac_hits(self, sym, chunk, K_bits, cols_of):
+    def _ac_hits(self, sym, chunk, K_bits, cols_of, row_shift):
         """Generic chunked DFA walk; returns sorted hit positions (may include e >= n).
         Mirrors FrontAC::scan / FrontACB::scan: the in-chunk strides start `off` symbols in
         front of the chunk so that they end exactly at the chunk end, preceded by the
@@ -113,7 +113,7 @@ class Emulator:
             for i in range(K):
                 idx |= ext[starts + hist + first + i] << (K_bits * i)
             ent = tab[state * cols + idx]
-            state = ent >> K
+            state = ent >> row_shift
             h = ent & ((1 << K) - 1)
             if t >= 0 and h.any():
                 for i in range(K):
@@ -151,7 +151,7 @@ class Emulator:
             sym = text.astype(np.int64)
             win = self._win16(text)
             if p.algo == acwm.AC:
-                hits = self._ac_hits(sym, 112, 2, 1 << (2 * p.stride))
+                hits = self._ac_hits(sym, 112, 2, 1 << (2 * p.stride), 2 * p.stride + 1)  # entry = row byte offset | hits
                 hits = hits[(hits >= m_min - 1) & (hits < n)]
                 if p.exact_front:
                     return int(hits.size), hits.astype(np.uint64)
@@ -173,7 +173,7 @@ class Emulator:
                 alpha = min(p.alphabet, 255)
                 cls = np.minimum(text.astype(np.int64), alpha)
                 lognc = int(p.n_classes).bit_length() - 1
-                hits = self._ac_hits(cls, 112, lognc, 1 << lognc)
+                hits = self._ac_hits(cls, 112, lognc, 1 << lognc, 1)
                 hits = hits[(hits >= m_min - 1) & (hits < n)]
                 if p.exact_front:
                     return int(hits.size), hits.astype(np.uint64)
