@@ -222,9 +222,13 @@ def run_ours(args):
 
     count_view = _device_count_tensor(torch, d_count_ptr, dev)  # the matcher's device-resident count
 
+    # the only thing that crosses NVLink is the per-GPU match count (8 bytes): exchanged inside the scan
+    # kernel through peer-mapped mailboxes; NCCL all_reduce is the fallback
+    fused_exchange = world > 1 and not args.nccl_count and sh.connect_peers(mt, dev)
+
     def step(i, want_positions=True):
         mt.scan_tensor(dev_texts[i % N_ROTATE], want_positions=want_positions, report_from=report_from)
-        if world > 1:  # the only thing that crosses NVLink: the per-GPU match count (8 bytes)
+        if world > 1 and not fused_exchange:
             count_buf.copy_(count_view)
             sh.allreduce_count_tensor(count_buf)
 
@@ -261,6 +265,10 @@ def run_ours(args):
     # ---- results of the last step (parity of the global count is a test, here it is reported)
     last_count, last_pos, _ = mt.fetch(cap=pos_cap, stream=stream)
     global_count = sh.allreduce_count(last_count, dev)
+    if fused_exchange:  # what the kernels exchanged must be what NCCL sums
+        fused_global = mt.fetch_global_count(stream)
+        assert fused_global == global_count, (fused_global, global_count)
+        mt.set_peers(0, 0, None)  # the legs below are per-rank (profiling, e2e): no exchange
 
     # ---- roofline: the scan kernel alone, CUDA events on the launching stream
     mt.set_profiling(True)
@@ -332,6 +340,9 @@ def run_ours(args):
                        "text_bytes_per_gpu": n, "halo_bytes": halo,
                        "l2": f"{N_ROTATE} distinct {args.text_mib} MiB texts cycled (working set > L2)",
                        "positions": "count + sorted uint64 positions produced every step",
+                       "count_exchange": ("none (1 GPU)" if world == 1 else
+                                          "in-kernel st.release.sys into NVLink peer mailboxes (torch symmetric memory)"
+                                          if fused_exchange else "NCCL all_reduce of the 8-byte count per step"),
                        "launch": "one cooperative kernel per step (scan + position ordering + result), no memset / finalize nodes",
                        "kernel": {k: info[k] for k in ("packed2bit", "stride", "depth", "exact_front", "n_rows",
                                                         "table_in_smem", "smem_bytes", "threads", "stages")}},
@@ -405,6 +416,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--text-mib", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-count", action="store_true", help="all-reduce the count with NCCL instead of in-kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

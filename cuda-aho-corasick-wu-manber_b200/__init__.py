@@ -87,6 +87,8 @@ def lib():
         L.acwm_last_kernel_seconds.restype = C.c_double
         L.acwm_last_kernel_seconds.argtypes = [C.c_void_p]
         L.acwm_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.acwm_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, _u64p]
+        L.acwm_fetch_global_count.argtypes = [C.c_void_p, _u64p, C.c_void_p]
         L.acwm_profiled_seconds.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.acwm_launch_count.restype = C.c_ulonglong
         L.acwm_launch_count.argtypes = [C.c_void_p]
@@ -219,6 +221,19 @@ class Matcher:
                     allow=(ERR_OVERFLOW,) if allow_overflow else ())
         self.last_rc = rc
         return int(count.value), pos[:int(nw.value)]
+
+    def set_peers(self, rank: int, world: int, mailbox_ptrs):
+        """In-kernel count exchange over peer memory (see acwm_set_peers); None / world<=1 = off."""
+        if not mailbox_ptrs or world <= 1:
+            _check(lib().acwm_set_peers(self._h, 0, 0, None))
+            return
+        arr = (C.c_uint64 * world)(*[int(p) for p in mailbox_ptrs])
+        _check(lib().acwm_set_peers(self._h, rank, world, arr))
+
+    def fetch_global_count(self, stream: int = 0) -> int:
+        g = C.c_uint64()
+        _check(lib().acwm_fetch_global_count(self._h, C.byref(g), C.c_void_p(stream)))
+        return int(g.value)
 
     def set_profiling(self, on: bool):
         _check(lib().acwm_set_profiling(self._h, int(on)))

@@ -137,7 +137,7 @@ static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
 // Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
 // cooperative kernel that scans, orders the positions and publishes the result block.
 static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
-		uint64_t tile_hi, int want_positions, int append, cudaStream_t st) {
+		uint64_t tile_hi, int want_positions, int append, int exchange, cudaStream_t st) {
 	const Compiled &c = mt->c;
 	ScanArgs a;
 	memset(&a, 0, sizeof(a));
@@ -168,6 +168,13 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.epoch = mt->epoch++;
 	a.want_positions = want_positions;
 	a.append = append;
+	if (exchange && mt->peer_world > 1) {
+		a.world = mt->peer_world;
+		a.rank = mt->peer_rank;
+		a.xepoch = ++mt->xepoch; // starts at 1: a zeroed mailbox never matches
+		for (uint32_t r = 0; r < mt->peer_world; r++)
+			a.peers[r] = reinterpret_cast<unsigned long long *>(mt->peer_ptrs[r]);
+	}
 	const uint32_t threads = c.info.threads, warps = threads / 32;
 	const uint64_t ntl = tile_hi - tile_lo;
 	// every CTA owns a contiguous span of whole "rounds" (one tile per warp)
@@ -250,7 +257,7 @@ int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64
 				CU(cudaEventCreate(&e));
 		CU(cudaEventRecord(mt->ev_prof[0], st));
 	}
-	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, 0, st)))
+	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, 0, 1, st)))
 		return rc;
 	if (mt->profiling)
 		CU(cudaEventRecord(mt->ev_prof[1], st));
@@ -338,7 +345,7 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
 		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
 		if ((rc = launch_scan(mt, mt->d_text, n, 0, std::min(n_tiles, ci * chunk_tiles),
-					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, mt->s_scan)))
+					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, 0, mt->s_scan)))
 			return rc;
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
 	}
@@ -355,6 +362,36 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 }
 
 double acwm_last_kernel_seconds(const acwm_matcher *mt) { return mt ? mt->last_kernel_s : 0.0; }
+
+int acwm_set_peers(acwm_matcher *mt, uint32_t rank, uint32_t world, const uint64_t *mailboxes) {
+	if (!mt)
+		return set_error(ACWM_ERR_INVALID, "matcher == NULL");
+	if (world <= 1 || !mailboxes) {
+		mt->peer_world = mt->peer_rank = 0;
+		return ACWM_OK;
+	}
+	if (world > kMaxPeers || rank >= world)
+		return set_error(ACWM_ERR_INVALID, "acwm_set_peers: world > 16 or rank >= world");
+	for (uint32_t r = 0; r < world; r++) {
+		if (!mailboxes[r])
+			return set_error(ACWM_ERR_INVALID, "acwm_set_peers: NULL mailbox");
+		mt->peer_ptrs[r] = mailboxes[r];
+	}
+	mt->peer_world = world;
+	mt->peer_rank = rank;
+	mt->xepoch = 0;
+	return ACWM_OK;
+}
+
+int acwm_fetch_global_count(acwm_matcher *mt, uint64_t *global_count, void *stream) {
+	if (!mt || !mt->uploaded || !global_count)
+		return set_error(ACWM_ERR_INVALID, "matcher not uploaded / NULL argument");
+	cudaStream_t st = (cudaStream_t) stream;
+	CU(cudaMemcpyAsync(mt->h_res, &mt->d_ctl->result, sizeof(Result), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	*global_count = mt->h_res->global_count;
+	return ACWM_OK;
+}
 
 int acwm_set_profiling(acwm_matcher *mt, int on) {
 	if (!mt)

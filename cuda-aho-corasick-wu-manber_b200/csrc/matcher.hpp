@@ -48,6 +48,9 @@ struct acwm_matcher {
 	std::array<cudaEvent_t, 2> ev_prof{};
 	bool profiling = false;
 	uint32_t epoch = 0;
+	// multi-GPU count exchange (acwm_set_peers)
+	uint32_t peer_world = 0, peer_rank = 0, xepoch = 0;
+	uint64_t peer_ptrs[acwm::kMaxPeers] = {};
 	double last_kernel_s = 0;
 	int last_want_positions = 0;
 	unsigned long long launches = 0;

@@ -14,6 +14,7 @@ struct Result {
 	unsigned long long written;  // positions placed in the output (cumulative)
 	unsigned int bad_text;       // OR of (byte & 0xFC) over the text, 2-bit path
 	unsigned int overflow;       // more matches than position capacity
+	unsigned long long global_count; // sum of `count` over the ranks of the peer exchange (== count without peers)
 };
 
 // Working counters of the launch in flight.  Two copies: launch k uses work[k & 1] and
@@ -57,11 +58,23 @@ struct ScanArgs {
 	uint32_t stages;             // ring depth of the per-warp tile pipeline
 	uint32_t cnt_cap;            // per-tile counts of the first cnt_cap tiles of a span live in shared memory
 	uint32_t epoch;              // launch number of this matcher: selects the Work copy
+	// multi-GPU count exchange over NVLink peer memory: every rank's mailbox is uint64[2][world]
+	uint32_t world, rank, xepoch;
+	unsigned long long *peers[kMaxPeers];
 	int want_positions;
 	int append;                  // 1: add to ctl->result instead of replacing it (chunked host text)
 };
 
 constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 

@@ -15,6 +15,9 @@
 //               the CTA's match count; the last CTA to arrive writes the result block.  The
 //               working counters are double-buffered by launch parity, each launch clears its
 //               successor's copy (no memset node between scans).
+//   4. exchange (multi-GPU) the publishing thread stores the rank's count into every peer's mailbox
+//               over NVLink (st.release.sys on peer-mapped memory) and, after the scatter, sums the
+//               mailbox of its own GPU: the all-reduce of the 8-byte count without another launch.
 #pragma once
 #include "scan_common.cuh"
 
@@ -344,6 +347,19 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	}
 
 	// ---- arrive: count + grid barrier + exit ticket in one atomic; the last CTA publishes
+	bool publisher = false;
+	// sum of the counts every rank left in our mailbox for this exchange epoch
+	auto collect_peers = [&]() {
+		unsigned long long sum = 0;
+		const unsigned long long *box = a.peers[a.rank] + (a.xepoch & 1u) * a.world;
+		for (uint32_t r = 0; r < a.world; r++) {
+			unsigned long long v;
+			while (((v = ld_acquire_sys_u64(box + r)) >> kArriveShift) != (a.xepoch & 0xffffu))
+				__nanosleep(64);
+			sum += v & ((1ull << kArriveShift) - 1);
+		}
+		a.ctl->result.global_count = sum;
+	};
 	if (threadIdx.x == 0) {
 		Work *other = &a.ctl->work[(a.epoch + 1u) & 1u];
 		if (blockIdx.x == 0) { // the successor launch's counters (its predecessor -- us -- is the only one that could still use them)
@@ -383,6 +399,14 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			res->written = r_written;
 			res->bad_text = old_bad | __ldcg(&wk->bad_text);
 			res->overflow = r_ovf;
+			if (a.world > 1) { // hand this launch's count to every rank (ours included)
+				const unsigned long long tagged = ((unsigned long long) (a.xepoch & 0xffffu) << kArriveShift) | cnt;
+				const uint32_t slot = (a.xepoch & 1u) * a.world + a.rank;
+				for (uint32_t r = 0; r < a.world; r++)
+					st_release_sys_u64(a.peers[r] + slot, tagged);
+				publisher = true;
+			} else
+				res->global_count = old_count + cnt;
 		}
 		if (a.want_positions) {
 			while ((ld_acquire_u64(&wk->arrive) >> kArriveShift) < G)
@@ -390,8 +414,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			__threadfence();
 		}
 	}
-	if (!a.want_positions)
+	if (!a.want_positions) {
+		if (publisher)
+			collect_peers();
 		return;
+	}
 	__syncthreads();
 
 	// ---- order, part 2: span bases = exclusive prefix of the per-CTA totals, then the scatter
@@ -438,6 +465,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		if (at < a.cap)
 			a.positions[at] = tile * kTile + pos - a.data_lo;
 	}
+	if (publisher) // the peers' counts have had the whole scatter to arrive
+		collect_peers();
 }
 
 // ------------------------------------------------------------ launch helper

@@ -7,8 +7,12 @@ overlapping chunks, main.c:656 MPI_Reduce of the count):
   scans text[r*c, min((r+1)*c + m_max-1, n)), c = ceil(n / world);
 * every rank scans its own shard with the same replicated tables -- no data-path
   collective;
-* only the per-rank match COUNT crosses the interconnect: one ``all_reduce(SUM)`` of a
-  uint64 (as int64) over NCCL/NVLink (gloo in the CPU tests);
+* only the per-rank match COUNT crosses the interconnect.  On GPUs the exchange is fused into
+  the scan kernel: ``connect_peers`` gives every rank a mailbox in torch symmetric memory
+  (peer-mapped over NVLink) and the kernel's publishing thread stores its 8-byte count into
+  all mailboxes and sums its own (``acwm_set_peers``) -- no extra launch per scan.  The NCCL
+  ``all_reduce(SUM)`` of a uint64 (as int64) remains as the fallback and as the cross-check
+  (gloo in the CPU tests);
 * positions stay per rank (shard-local offsets + the shard start = global, already
   sorted); ``gather_positions`` brings them to rank 0's host memory on request.
 """
@@ -24,6 +28,37 @@ def shard_of(n: int, world: int, rank: int, m_max: int):
     start, length = shard_bounds(n, world, rank, m_max - 1)
     # ranks > 0 own match ends >= start + m_max - 1 (the previous rank's halo covers the rest)
     return start, length, (m_max - 1 if rank > 0 else 0)
+
+
+def connect_peers(matcher, device=None) -> bool:
+    """Collective: set up the in-kernel count exchange for `matcher` over the default process group.
+    Returns False (and leaves the matcher on the NCCL path) if symmetric memory is unavailable."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+        return False
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ok = True
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        box = symm_mem.empty(2 * world, dtype=torch.int64, device=dev)
+        box.zero_()
+        hdl = symm_mem.rendezvous(box, dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001 -- any failure means "no peer memory here"
+        ok, box, hdl, ptrs = False, None, None, None
+        if rank == 0:
+            print(f"[sharding] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all_reduce", flush=True)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # also the barrier that orders the zero-fill before any exchange
+    if int(flag.item()) != 1:
+        matcher.set_peers(0, 0, None)
+        return False
+    matcher.set_peers(rank, world, ptrs)
+    matcher._mailbox = (box, hdl)  # keep the mapping alive
+    return True
 
 
 def allreduce_count(local_count: int, device=None) -> int:

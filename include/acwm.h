@@ -137,6 +137,16 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
  * its kernels: cuda/cuda_wm.cu:264-289) of the last acwm_search_host call. */
 double acwm_last_kernel_seconds(const acwm_matcher *mt);
 
+/* Multi-GPU count exchange inside the scan kernel (replaces MPI_Reduce of the count, main.c:656,
+ * and the NCCL all-reduce it would otherwise take): every rank owns a zero-initialised mailbox of
+ * uint64[2][world] in peer-accessible device memory (NVLink; e.g. torch symmetric memory);
+ * mailboxes[r] is rank r's mailbox AS MAPPED IN THIS PROCESS.  From then on every
+ * acwm_scan_device stores the launch's count into all mailboxes and leaves the sum over the
+ * ranks in the result block (acwm_fetch_global_count).  All ranks must issue the same sequence
+ * of acwm_scan_device calls (SPMD), like a collective.  world <= 1 or NULL switches it off. */
+int acwm_set_peers(acwm_matcher *mt, uint32_t rank, uint32_t world, const uint64_t *mailboxes);
+int acwm_fetch_global_count(acwm_matcher *mt, uint64_t *global_count, void *stream);
+
 /* Bench instrumentation: with profiling on, acwm_scan_device brackets the scan kernel and
  * the finalize kernels with CUDA events on the caller's stream; acwm_profiled_seconds
  * waits for the last profiled scan and returns the two durations. */
