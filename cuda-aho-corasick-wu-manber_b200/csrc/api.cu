@@ -193,6 +193,14 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	return ACWM_OK;
 }
 
+// Sum of the mailbox for the last exchange epoch (the scan kernels collect epoch x-1 while they run epoch x).
+__global__ void collect_last_kernel(Control *ctl, const unsigned long long *box, uint32_t world, uint32_t x) {
+	if (ctl->result.global_epoch != x) {
+		ctl->result.global_count = collect_mailbox(box, world, x);
+		ctl->result.global_epoch = x;
+	}
+}
+
 } // namespace acwm
 
 using namespace acwm;
@@ -387,6 +395,12 @@ int acwm_fetch_global_count(acwm_matcher *mt, uint64_t *global_count, void *stre
 	if (!mt || !mt->uploaded || !global_count)
 		return set_error(ACWM_ERR_INVALID, "matcher not uploaded / NULL argument");
 	cudaStream_t st = (cudaStream_t) stream;
+	if (mt->peer_world > 1 && mt->xepoch) { // the scan kernels run the exchange one scan behind: finish the last one
+		collect_last_kernel<<<1, 1, 0, st>>>(mt->d_ctl, reinterpret_cast<const unsigned long long *>(mt->peer_ptrs[mt->peer_rank]),
+				mt->peer_world, mt->xepoch);
+		CU(cudaGetLastError());
+		mt->launches++;
+	}
 	CU(cudaMemcpyAsync(mt->h_res, &mt->d_ctl->result, sizeof(Result), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	*global_count = mt->h_res->global_count;

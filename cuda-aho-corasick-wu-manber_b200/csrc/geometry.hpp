@@ -19,6 +19,7 @@ constexpr uint32_t kMaxDepthBytes = 64;             // AC bytes path: warm-up de
 constexpr uint32_t kPackWords = 1 + kTile / 16 + 3; // 2-bit copy of the tile (+16 symbols of history, + pad) = 228 words
 constexpr uint32_t kMaxStages = 4;
 constexpr uint32_t kMaxPeers = 16;                  // ranks of the in-kernel count exchange
+constexpr uint32_t kPeerRing = 4;                   // mailbox slots per rank pair: epochs in flight
 constexpr uint32_t kListCap = 64;                   // per-warp list of match positions of one tile (cooperative stores)
 
 // per-warp shared memory: ring of raw tiles, (2-bit path) 2-bit copy of the current tile for the

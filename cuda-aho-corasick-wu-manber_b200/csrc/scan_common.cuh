@@ -15,6 +15,8 @@ struct Result {
 	unsigned int bad_text;       // OR of (byte & 0xFC) over the text, 2-bit path
 	unsigned int overflow;       // more matches than position capacity
 	unsigned long long global_count; // sum of `count` over the ranks of the peer exchange (== count without peers)
+	unsigned int global_epoch;   // exchange epoch global_count belongs to
+	unsigned int pad;
 };
 
 // Working counters of the launch in flight.  Two copies: launch k uses work[k & 1] and
@@ -58,7 +60,7 @@ struct ScanArgs {
 	uint32_t stages;             // ring depth of the per-warp tile pipeline
 	uint32_t cnt_cap;            // per-tile counts of the first cnt_cap tiles of a span live in shared memory
 	uint32_t epoch;              // launch number of this matcher: selects the Work copy
-	// multi-GPU count exchange over NVLink peer memory: every rank's mailbox is uint64[2][world]
+	// multi-GPU count exchange over NVLink peer memory: every rank's mailbox is uint64[kPeerRing][world]
 	uint32_t world, rank, xepoch;
 	unsigned long long *peers[kMaxPeers];
 	int want_positions;
@@ -67,13 +69,26 @@ struct ScanArgs {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
-	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// The mailbox word carries its own tag, so relaxed system-scope accesses are enough.
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
 	unsigned long long v;
-	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
+}
+// Sum of the counts every rank left in this GPU's mailbox for exchange epoch `x` (spins until all are in).
+__device__ __forceinline__ unsigned long long collect_mailbox(const unsigned long long *box, uint32_t world, uint32_t x) {
+	unsigned long long sum = 0;
+	const unsigned long long *slot = box + (x & (kPeerRing - 1)) * world;
+	for (uint32_t r = 0; r < world; r++) {
+		unsigned long long v;
+		while (((v = ld_relaxed_sys_u64(slot + r)) >> 48) != (x & 0xffffu))
+			__nanosleep(32);
+		sum += v & ((1ull << 48) - 1);
+	}
+	return sum;
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

@@ -16,8 +16,9 @@
 //               working counters are double-buffered by launch parity, each launch clears its
 //               successor's copy (no memset node between scans).
 //   4. exchange (multi-GPU) the publishing thread stores the rank's count into every peer's mailbox
-//               over NVLink (st.release.sys on peer-mapped memory) and, after the scatter, sums the
-//               mailbox of its own GPU: the all-reduce of the 8-byte count without another launch.
+//               over NVLink (system-scope stores on peer-mapped memory) and, at its very end, sums
+//               what the peers left in its own mailbox for the PREVIOUS scan: an all-reduce of the
+//               8-byte count, pipelined by one scan, without another launch or a lock-step wait.
 #pragma once
 #include "scan_common.cuh"
 
@@ -348,17 +349,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 
 	// ---- arrive: count + grid barrier + exit ticket in one atomic; the last CTA publishes
 	bool publisher = false;
-	// sum of the counts every rank left in our mailbox for this exchange epoch
+	// the previous scan's counts have had a whole scan to arrive (the last one is collected by acwm_fetch_global_count)
 	auto collect_peers = [&]() {
-		unsigned long long sum = 0;
-		const unsigned long long *box = a.peers[a.rank] + (a.xepoch & 1u) * a.world;
-		for (uint32_t r = 0; r < a.world; r++) {
-			unsigned long long v;
-			while (((v = ld_acquire_sys_u64(box + r)) >> kArriveShift) != (a.xepoch & 0xffffu))
-				__nanosleep(64);
-			sum += v & ((1ull << kArriveShift) - 1);
-		}
-		a.ctl->result.global_count = sum;
+		if (a.xepoch < 2)
+			return;
+		a.ctl->result.global_count = collect_mailbox(a.peers[a.rank], a.world, a.xepoch - 1);
+		a.ctl->result.global_epoch = a.xepoch - 1;
 	};
 	if (threadIdx.x == 0) {
 		Work *other = &a.ctl->work[(a.epoch + 1u) & 1u];
@@ -401,9 +397,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			res->overflow = r_ovf;
 			if (a.world > 1) { // hand this launch's count to every rank (ours included)
 				const unsigned long long tagged = ((unsigned long long) (a.xepoch & 0xffffu) << kArriveShift) | cnt;
-				const uint32_t slot = (a.xepoch & 1u) * a.world + a.rank;
+				const uint32_t slot = (a.xepoch & (kPeerRing - 1)) * a.world + a.rank;
 				for (uint32_t r = 0; r < a.world; r++)
-					st_release_sys_u64(a.peers[r] + slot, tagged);
+					st_relaxed_sys_u64(a.peers[r] + slot, tagged);
 				publisher = true;
 			} else
 				res->global_count = old_count + cnt;
@@ -465,7 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		if (at < a.cap)
 			a.positions[at] = tile * kTile + pos - a.data_lo;
 	}
-	if (publisher) // the peers' counts have had the whole scatter to arrive
+	if (publisher)
 		collect_peers();
 }
 

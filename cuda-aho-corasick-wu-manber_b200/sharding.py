@@ -42,7 +42,7 @@ def connect_peers(matcher, device=None) -> bool:
     try:
         import torch.distributed._symmetric_memory as symm_mem
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        box = symm_mem.empty(2 * world, dtype=torch.int64, device=dev)
+        box = symm_mem.empty(4 * world, dtype=torch.int64, device=dev)  # uint64[kPeerRing][world]
         box.zero_()
         hdl = symm_mem.rendezvous(box, dist.group.WORLD)
         ptrs = [int(p) for p in hdl.buffer_ptrs]

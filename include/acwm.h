@@ -139,11 +139,13 @@ double acwm_last_kernel_seconds(const acwm_matcher *mt);
 
 /* Multi-GPU count exchange inside the scan kernel (replaces MPI_Reduce of the count, main.c:656,
  * and the NCCL all-reduce it would otherwise take): every rank owns a zero-initialised mailbox of
- * uint64[2][world] in peer-accessible device memory (NVLink; e.g. torch symmetric memory);
+ * uint64[4][world] in peer-accessible device memory (NVLink; e.g. torch symmetric memory);
  * mailboxes[r] is rank r's mailbox AS MAPPED IN THIS PROCESS.  From then on every
- * acwm_scan_device stores the launch's count into all mailboxes and leaves the sum over the
- * ranks in the result block (acwm_fetch_global_count).  All ranks must issue the same sequence
- * of acwm_scan_device calls (SPMD), like a collective.  world <= 1 or NULL switches it off. */
+ * acwm_scan_device stores the launch's count into all mailboxes over NVLink and sums the
+ * previous scan's mailbox (the exchange runs one scan behind the scans, so no GPU waits for
+ * another in lock step); acwm_fetch_global_count completes the exchange of the LAST scan and
+ * returns its sum over the ranks.  All ranks must issue the same sequence of acwm_scan_device
+ * calls (SPMD), like a collective.  world <= 1 or NULL switches it off. */
 int acwm_set_peers(acwm_matcher *mt, uint32_t rank, uint32_t world, const uint64_t *mailboxes);
 int acwm_fetch_global_count(acwm_matcher *mt, uint64_t *global_count, void *stream);
 
