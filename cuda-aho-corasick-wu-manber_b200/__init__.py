@@ -38,7 +38,8 @@ class AcwmError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("smem_table_budget", C.c_uint32), ("force_stride", C.c_uint32), ("force_depth", C.c_uint32),
                 ("force_bytes_path", C.c_uint32), ("force_threads", C.c_uint32), ("force_stages", C.c_uint32),
-                ("force_f2_bits", C.c_uint32), ("force_r_bits", C.c_uint32)]
+                ("force_f2_bits", C.c_uint32), ("force_r_bits", C.c_uint32), ("force_smem_tables", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class Info(C.Structure):
@@ -55,8 +56,8 @@ class ScanParams(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in
                 ("algo", "packed2bit", "alphabet", "m_min", "m_max", "stride", "depth", "exact_front", "n_rows",
                  "f1_sh1", "f1_mult", "f1_sh2", "f1_words", "b2", "f2_mult", "f2_sh", "f2_words", "hb_mult",
-                 "hb_sh", "n_buckets", "n_entries", "n_classes", "r_mult", "r_sh", "r_entries", "r_entry_bytes")] + \
-               [("reserved", C.c_uint32 * 4)]
+                 "hb_sh", "n_buckets", "n_entries", "n_classes", "r_mult", "r_sh", "r_entries", "r_entry_bytes", "r_in_smem", "f2_in_smem")] + \
+               [("reserved", C.c_uint32 * 2)]
 
 
 VENTRY_DTYPE = np.dtype([("key", "<u4"), ("len", "<u4"), ("offset", "<u8")])

@@ -88,18 +88,31 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	mt->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
 	const Compiled &c = mt->c;
 	int rc;
-	if ((rc = dev_upload(&mt->d_front, c.front.data(), c.front.size())))
+	// all tables in ONE device allocation, so that a single access-policy window keeps them in L2
+	const struct {
+		const void *src;
+		size_t bytes;
+	} parts[6] = {{c.front.data(), c.front.size()}, {c.rmask.data(), c.rmask.size()},
+			{c.filter2.data(), c.filter2.size() * 4}, {c.bucket_start.data(), c.bucket_start.size() * 4},
+			{c.entries.data(), c.entries.size() * sizeof(acwm_ventry)}, {mt->ps.bytes.data(), mt->ps.bytes.size()}};
+	size_t off[6], total = 0;
+	for (int i = 0; i < 6; i++) {
+		off[i] = total;
+		total += (std::max<size_t>(parts[i].bytes, 16) + 255) & ~(size_t) 255;
+	}
+	if ((rc = dev_upload(&mt->d_tables, nullptr, total)))
 		return rc;
-	if ((rc = dev_upload(&mt->d_rmask, c.rmask.data(), c.rmask.size())))
-		return rc;
-	if ((rc = dev_upload(&mt->d_filter2, c.filter2.data(), c.filter2.size() * 4)))
-		return rc;
-	if ((rc = dev_upload(&mt->d_bucket_start, c.bucket_start.data(), c.bucket_start.size() * 4)))
-		return rc;
-	if ((rc = dev_upload(&mt->d_entries, c.entries.data(), c.entries.size() * sizeof(acwm_ventry))))
-		return rc;
-	if ((rc = dev_upload(&mt->d_patterns, mt->ps.bytes.data(), mt->ps.bytes.size())))
-		return rc;
+	CU(cudaMemset(mt->d_tables, 0, total));
+	for (int i = 0; i < 6; i++)
+		if (parts[i].bytes)
+			CU(cudaMemcpy(mt->d_tables + off[i], parts[i].src, parts[i].bytes, cudaMemcpyHostToDevice));
+	mt->tables_bytes = total;
+	mt->d_front = mt->d_tables + off[0];
+	mt->d_rmask = mt->d_tables + off[1];
+	mt->d_filter2 = reinterpret_cast<uint32_t *>(mt->d_tables + off[2]);
+	mt->d_bucket_start = reinterpret_cast<uint32_t *>(mt->d_tables + off[3]);
+	mt->d_entries = reinterpret_cast<acwm_ventry *>(mt->d_tables + off[4]);
+	mt->d_patterns = mt->d_tables + off[5];
 	CU(cudaMalloc((void **) &mt->d_ctl, sizeof(Control)));
 	CU(cudaMemset(mt->d_ctl, 0, sizeof(Control)));
 	CU(cudaMallocHost((void **) &mt->h_res, sizeof(Result)));
@@ -108,10 +121,10 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	CU(cudaStreamCreateWithFlags(&mt->s_scan, cudaStreamNonBlocking));
 	for (auto &e : mt->ev_copy)
 		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-	// a front table that lives in global memory is kept L2-resident with an access-policy window
-	if (!c.info.table_in_smem && mt->l2_persist_max) {
-		const size_t want = std::min(c.front.size(), mt->l2_persist_max);
-		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+	// tables read from global memory by the kernels are kept L2-resident (access-policy window, apply_l2_window)
+	mt->l2_tables = !c.info.table_in_smem || (c.prm.r_entries && !c.prm.r_in_smem) || (c.prm.f2_words && !c.prm.f2_in_smem);
+	if (mt->l2_tables && mt->l2_persist_max) {
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(mt->tables_bytes, mt->l2_persist_max));
 		(void) cudaGetLastError();
 	}
 	mt->uploaded = true;
@@ -121,17 +134,19 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 }
 
 static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
-	if (mt->c.info.table_in_smem || !mt->l2_window_max)
+	if (!mt->l2_tables || !mt->l2_window_max || mt->l2_window_stream == (void *) st)
 		return;
 	cudaStreamAttrValue v;
 	memset(&v, 0, sizeof(v));
-	v.accessPolicyWindow.base_ptr = mt->d_front;
-	v.accessPolicyWindow.num_bytes = std::min(mt->c.front.size(), mt->l2_window_max);
-	v.accessPolicyWindow.hitRatio = 1.0f;
+	const size_t win = std::min(mt->tables_bytes, mt->l2_window_max);
+	v.accessPolicyWindow.base_ptr = mt->d_tables;
+	v.accessPolicyWindow.num_bytes = win;
+	v.accessPolicyWindow.hitRatio = mt->l2_persist_max ? (float) std::min(1.0, (double) mt->l2_persist_max / (double) win) : 1.0f;
 	v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
 	v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
 	cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
 	(void) cudaGetLastError();
+	mt->l2_window_stream = (void *) st; // set once per stream, not once per scan
 }
 
 // Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
@@ -441,12 +456,7 @@ void acwm_free(acwm_matcher *mt) {
 		return;
 	if (mt->uploaded) {
 		cudaSetDevice(mt->device);
-		cudaFree(mt->d_front);
-		cudaFree(mt->d_filter2);
-		cudaFree(mt->d_rmask);
-		cudaFree(mt->d_bucket_start);
-		cudaFree(mt->d_entries);
-		cudaFree(mt->d_patterns);
+		cudaFree(mt->d_tables);
 		cudaFree(mt->d_ctl);
 		cudaFree(mt->d_cta_total);
 		if (mt->d_staging)

@@ -26,6 +26,10 @@ struct acwm_matcher {
 	bool uploaded = false;
 	int device = -1, sm_count = 0;
 	size_t l2_persist_max = 0, l2_window_max = 0;
+	uint8_t *d_tables = nullptr; // one allocation: front | offset masks | stage-2 bitmap | buckets | entries | patterns
+	size_t tables_bytes = 0;
+	bool l2_tables = false;
+	void *l2_window_stream = nullptr;
 	uint8_t *d_front = nullptr;
 	uint8_t *d_rmask = nullptr;
 	uint32_t *d_filter2 = nullptr;

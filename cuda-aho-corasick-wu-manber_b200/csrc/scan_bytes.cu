@@ -120,7 +120,7 @@ struct FrontACB : BytesKey {
 };
 
 // ------------------------------------------------------------ front end: WM over bytes
-template <int S>
+template <int S, bool GLOBAL>
 struct FrontWMB : BytesKey {
 	static constexpr int kSamples = (int) kLane / S; // 112 / 56 / 28 / 14 / 7
 	static constexpr int kWords = (kSamples + 31) / 32;
@@ -141,7 +141,7 @@ struct FrontWMB : BytesKey {
 	}
 	__device__ __forceinline__ void init(const uint8_t *smem_tab, const uint8_t *rmask, const ScanArgs &a) {
 		rmk = rmask;
-		bm = reinterpret_cast<const uint32_t *>(smem_tab);
+		bm = reinterpret_cast<const uint32_t *>(GLOBAL ? a.front : smem_tab);
 		sh1 = a.prm.f1_sh1;
 		mult = a.prm.f1_mult;
 		sh2 = a.prm.f1_sh2;
@@ -166,7 +166,7 @@ struct FrontWMB : BytesKey {
 			const uint32_t hi = (bh & 3) ? __byte_perm(X[bh >> 2], X[(bh >> 2) + 1], 0x3210 + 0x1111 * (bh & 3)) : X[bh >> 2];
 			const uint64_t blk = (((uint64_t) hi << 32) | lo) >> sh1;
 			const uint32_t idx = (uint32_t) (mix64(blk) * mult) >> sh2;
-			const uint32_t word = bm[idx >> 5];
+			const uint32_t word = GLOBAL ? __ldg(bm + (idx >> 5)) : bm[idx >> 5];
 			hw[j / 32] += ((word >> (idx & 31)) & 1u) << (j % 32);
 		}
 	}
@@ -193,11 +193,15 @@ cudaError_t launch_scan_bytes(const ScanArgs &a, uint32_t threads, uint32_t smem
 				  : launch_front<FrontACB<false>, false>(a, threads, smem, grid, st);
 	}
 	switch (p.stride) {
-	case 16: return launch_front<FrontWMB<16>, false>(a, threads, smem, grid, st);
-	case 8: return launch_front<FrontWMB<8>, false>(a, threads, smem, grid, st);
-	case 4: return launch_front<FrontWMB<4>, false>(a, threads, smem, grid, st);
-	case 2: return launch_front<FrontWMB<2>, false>(a, threads, smem, grid, st);
-	case 1: return launch_front<FrontWMB<1>, false>(a, threads, smem, grid, st);
+#define ACWM_WMB(S)                                                                                   \
+	case S: return a.front_in_smem ? launch_front<FrontWMB<S, false>, false>(a, threads, smem, grid, st) \
+								   : launch_front<FrontWMB<S, true>, false>(a, threads, smem, grid, st);
+	ACWM_WMB(16)
+	ACWM_WMB(8)
+	ACWM_WMB(4)
+	ACWM_WMB(2)
+	ACWM_WMB(1)
+#undef ACWM_WMB
 	default: return cudaErrorInvalidValue;
 	}
 }

@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	unsigned long long *s_misc = reinterpret_cast<unsigned long long *>(smem + 32);  // [0] cursor, [1] append base
 	uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + 64); // 33 words
 	const uint32_t front_smem = a.front_in_smem ? ((a.front_bytes + 15u) & ~15u) : 0u;
-	const uint32_t rm_bytes = EXACT ? 0u : ((a.prm.r_entries * a.prm.r_entry_bytes + 15u) & ~15u);
-	const uint32_t f2_bytes = EXACT ? 0u : ((a.prm.f2_words * 4u + 15u) & ~15u);
+	// tables too large for shared memory stay in global memory (L2-resident: access-policy window + evict_first text)
+	const uint32_t rm_bytes = (EXACT || !a.prm.r_in_smem) ? 0u : ((a.prm.r_entries * a.prm.r_entry_bytes + 15u) & ~15u);
+	const uint32_t f2_bytes = (EXACT || !a.prm.f2_in_smem) ? 0u : ((a.prm.f2_words * 4u + 15u) & ~15u);
 	uint8_t *s_front = smem + kSmemReserve;
 	uint8_t *s_rmask = s_front + front_smem;
 	uint32_t *s_f2 = reinterpret_cast<uint32_t *>(s_rmask + rm_bytes);
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	Front fr;
 	if (tab_bytes)
 		mbar_wait(tab_bar, 0);
-	fr.init(s_front, s_rmask, a);
+	const uint32_t *f2 = a.prm.f2_in_smem ? s_f2 : a.filter2;
+	fr.init(s_front, a.prm.r_in_smem ? s_rmask : a.rmask, a);
 
 	for (uint32_t slot = 0;; slot = slot + 1 == stages ? 0 : slot + 1) {
 		const uint32_t idx = s_tid[slot];
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 						rm &= rm - 1;
 						const uint32_t key = Front::key_at(a, buf, pk, lane * kLane + p);
 						const uint32_t i2 = (uint32_t) (key * a.prm.f2_mult) >> a.prm.f2_sh;
-						if ((s_f2[i2 >> 5] >> (i2 & 31)) & 1u) {
+						if ((f2[i2 >> 5] >> (i2 & 31)) & 1u) {
 							const uint32_t mult = verify_window(a, key, tile_start + lane * kLane + p);
 							if (mult) {
 								const uint32_t bit = 1u << (p & 31);
@@ -497,9 +499,13 @@ static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid,
 
 template <class Front, bool EXACT>
 static cudaError_t launch_front(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st) {
+	if constexpr (Front::kPacked) { // the bytes path needs two raw slots per warp: at most 16 warps fit
+		if (threads == 1024)
+			return launch_shape<Front, EXACT, 1024>(a, smem, grid, st);
+		if (threads == 768)
+			return launch_shape<Front, EXACT, 768>(a, smem, grid, st);
+	}
 	switch (threads) {
-	case 1024: return launch_shape<Front, EXACT, 1024>(a, smem, grid, st);
-	case 768: return launch_shape<Front, EXACT, 768>(a, smem, grid, st);
 	case 512: return launch_shape<Front, EXACT, 512>(a, smem, grid, st);
 	case 384: return launch_shape<Front, EXACT, 384>(a, smem, grid, st);
 	case 256: return launch_shape<Front, EXACT, 256>(a, smem, grid, st);

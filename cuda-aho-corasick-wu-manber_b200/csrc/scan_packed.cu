@@ -183,7 +183,9 @@ struct FrontAC : PackedKey {
 };
 
 // ------------------------------------------------------------ front end: WM, sampled every S symbols
-template <int S, bool HASHED>
+// MODE 0: direct-indexed bitmap in shared memory, 1: hashed bitmap in shared memory,
+//      2: bitmap in global memory (L2-resident; direct index = multiplier 1, shift 0)
+template <int S, int MODE>
 struct FrontWM : PackedKey {
 	static constexpr int kSamples = (int) kLane / S; // 112 / 56 / 28 / 14 / 7
 	static constexpr int kWords = (kSamples + 31) / 32;
@@ -196,7 +198,7 @@ struct FrontWM : PackedKey {
 	uint32_t hw[kWords];
 
 	__device__ __forceinline__ void init(const uint8_t *table, const uint8_t *rmask, const ScanArgs &a) {
-		bm = reinterpret_cast<const uint32_t *>(table);
+		bm = reinterpret_cast<const uint32_t *>(MODE == 2 ? a.front : table);
 		rmk = rmask;
 		sh1 = a.prm.f1_sh1;
 		mult = a.prm.f1_mult;
@@ -229,9 +231,9 @@ struct FrontWM : PackedKey {
 			const int wi = bit >> 5, sh = bit & 31;
 			const uint32_t v = sh ? __funnelshift_r(W[wi], W[wi + 1], sh) : W[wi];
 			uint32_t idx = v >> sh1;
-			if (HASHED)
+			if (MODE != 0)
 				idx = (idx * mult) >> sh2;
-			const uint32_t word = bm[idx >> 5];
+			const uint32_t word = MODE == 2 ? __ldg(bm + (idx >> 5)) : bm[idx >> 5];
 			hw[j / 32] += ((word >> (idx & 31)) & 1u) << (j % 32);
 		}
 	}
@@ -261,11 +263,12 @@ cudaError_t launch_scan_packed(const ScanArgs &a, uint32_t threads, uint32_t sme
 		default: return cudaErrorInvalidValue;
 		}
 	}
-	const bool hashed = p.f1_mult != 1;
+	const int mode = !a.front_in_smem ? 2 : (p.f1_mult != 1 ? 1 : 0);
 	switch (p.stride) {
 #define ACWM_WM(S)                                                                        \
-	case S: return hashed ? launch_front<FrontWM<S, true>, false>(a, threads, smem, grid, st) \
-						  : launch_front<FrontWM<S, false>, false>(a, threads, smem, grid, st);
+	case S: return mode == 2 ? launch_front<FrontWM<S, 2>, false>(a, threads, smem, grid, st) \
+		 : mode == 1 ? launch_front<FrontWM<S, 1>, false>(a, threads, smem, grid, st)         \
+					 : launch_front<FrontWM<S, 0>, false>(a, threads, smem, grid, st);
 	ACWM_WM(16)
 	ACWM_WM(8)
 	ACWM_WM(4)

@@ -107,9 +107,11 @@ static void build_verify(const PatternSet &ps, bool packed, const acwm_options &
 	const uint32_t key_bits = packed ? 2 * b2 : 32;
 	// ~1.5 % of the probes pass (a pass costs dependent L2 loads in the buckets); a larger bitmap
 	// measured no faster (profiles/r01d_tune.csv) and every CTA has to load it
-	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 64), 13), 18);
+	// shared memory up to 2^18 bits (32 KiB); larger sets get an L2-resident bitmap of up to 2^26 bits
+	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 64), 13),
+			opts.force_smem_tables ? 18 : 26);
 	if (opts.force_f2_bits)
-		f2bits = std::min<uint32_t>(std::max<uint32_t>(opts.force_f2_bits, 13), 19);
+		f2bits = std::min<uint32_t>(std::max<uint32_t>(opts.force_f2_bits, 13), 26);
 	if (packed && key_bits <= f2bits) {
 		f2bits = std::max<uint32_t>(key_bits, 5);
 		prm.f2_mult = 1;
@@ -118,7 +120,8 @@ static void build_verify(const PatternSet &ps, bool packed, const acwm_options &
 		prm.f2_mult = kMultF2;
 		prm.f2_sh = 32 - f2bits;
 	}
-	prm.f2_words = (1u << f2bits) / 32;
+	prm.f2_in_smem = f2bits <= 18 ? 1 : 0;
+	prm.f2_words = (uint32_t) (((uint64_t) 1 << f2bits) / 32);
 	c.filter2.assign(prm.f2_words, 0);
 	// buckets
 	const uint32_t hbits = std::max<uint32_t>(ceil_log2((uint64_t) pd * 2), 4);
@@ -403,53 +406,85 @@ static int compile_ac_bytes(const PatternSet &ps, const acwm_options &opts, uint
 // (wu/wu.c:126-128 computes the same minimum distance).  Every occurrence ending at
 // e is covered by the sample c = e - r, r = e mod-aligned distance < s, because
 // B <= m_min - s + 1 keeps the block inside the occurrence.
+// Where a WM stage-1 bitmap for stride s would live and how selective it would be.
+struct WmPlan {
+	uint32_t s = 0, B = 0, fbits = 0;
+	bool direct = false, in_smem = true;
+	double cost = 1e30;
+};
+
+static WmPlan plan_wm_stride(const PatternSet &ps, bool packed, uint32_t s, uint32_t smem_fbits_max, bool allow_global) {
+	const uint32_t pd = ps.size();
+	const uint32_t Bcap = packed ? 16 : 8;
+	const uint32_t B = std::min<uint32_t>(Bcap, ps.m_min - s + 1);
+	const uint32_t key_bits = packed ? 2 * B : 8 * B; // bytes path: the block is mixed to 32 bits and always hashed
+	const double entries = (double) s * pd;
+	WmPlan best;
+	auto consider = [&](uint32_t fbits, bool direct, bool in_smem) {
+		// a sample is a candidate with probability `rate` and then costs its lane ~60 slots (the rest of the
+		// warp waits) plus ~40 per offset it has to probe: about `load` offsets, at most s
+		const double load = entries / std::pow(2.0, (double) std::min(fbits, key_bits));
+		const double rate = 1.0 - std::exp(-load);
+		// per symbol: ~8 lane-instructions per sample (+4 when the bitmap word comes from L2)
+		const double cost = ((packed ? 8.0 : 10.0) + (in_smem ? 0.0 : 4.0) + rate * 60.0
+									+ std::min<double>(s, load) * 40.0) / s;
+		if (cost < best.cost - 1e-9) {
+			best.s = s;
+			best.B = B;
+			best.fbits = fbits;
+			best.direct = direct;
+			best.in_smem = in_smem;
+			best.cost = cost;
+		}
+	};
+	if (packed && key_bits <= smem_fbits_max)
+		consider(std::max<uint32_t>(key_bits, 5), true, true);
+	else if (!packed && key_bits < 13)
+		consider(13, false, true);
+	else
+		consider(std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) (entries * 32)), 13), smem_fbits_max), false, true);
+	if (allow_global) { // L2-resident bitmap: up to 2^26 bits = 8 MiB
+		if (packed && key_bits <= 26 && key_bits > smem_fbits_max)
+			consider(key_bits, true, false);
+		else if (key_bits > smem_fbits_max)
+			consider(std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) (entries * 256)), smem_fbits_max + 1), 26),
+					false, false);
+	}
+	return best;
+}
+
 static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packed, uint32_t budget, Compiled &c,
 		std::string &err) {
 	acwm_scan_params &prm = c.prm;
 	const uint32_t pd = ps.size();
-	const uint32_t Bcap = packed ? 16 : 8;
-	const double sigma_bits = packed ? 2.0 : std::log2((double) ps.alphabet);
-	const uint32_t max_fbits = std::min<uint32_t>(ceil_log2((uint64_t) budget * 8 + 1) - 1, 20);
-	double best_cost = 1e30;
-	uint32_t bestS = 0;
+	const uint32_t smem_fbits_max = std::min<uint32_t>(ceil_log2((uint64_t) budget * 8 + 1) - 1, 19);
+	WmPlan plan;
 	for (uint32_t s : {16u, 8u, 4u, 2u, 1u}) {
 		if (opts.force_stride && opts.force_stride != s)
 			continue;
 		if (s > ps.m_min)
 			continue;
-		const uint32_t B = std::min<uint32_t>(Bcap, ps.m_min - s + 1);
-		const double space_bits = std::min<double>(B * sigma_bits, (double) max_fbits);
-		const double load = (double) s * pd / std::pow(2.0, space_bits);
-		const double rate = 1.0 - std::exp(-load);
-		// per symbol: ~8 lane-instructions per sample + `rate` candidates per sample, each handled by its
-		// own lane while the rest of the warp waits (~150 lane-instruction slots)
-		const double cost = ((packed ? 8.0 : 10.0) + rate * 150.0) / s;
-		if (cost < best_cost - 1e-9) {
-			best_cost = cost;
-			bestS = s;
-		}
+		const WmPlan p = plan_wm_stride(ps, packed, s, smem_fbits_max, !opts.force_smem_tables);
+		if (p.cost < plan.cost - 1e-9)
+			plan = p;
 	}
-	if (!bestS) {
+	if (!plan.s) {
 		err = "WM: no sampling stride fits (pattern shorter than the forced stride?)";
 		return ACWM_ERR_INVALID;
 	}
-	const uint32_t s = bestS;
-	const uint32_t B = std::min<uint32_t>(Bcap, ps.m_min - s + 1);
+	const uint32_t s = plan.s, B = plan.B, fbits = plan.fbits;
 	prm.stride = s;
 	prm.depth = B;
 	prm.exact_front = 0;
-	uint32_t fbits;
-	if (packed && 2 * B <= max_fbits) {
-		fbits = std::max<uint32_t>(2 * B, 5);
+	if (plan.direct) {
 		prm.f1_mult = 1;
 		prm.f1_sh2 = 0;
 	} else {
-		fbits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 32), 13), max_fbits);
 		prm.f1_mult = kMultF1;
 		prm.f1_sh2 = 32 - fbits;
 	}
 	prm.f1_sh1 = packed ? 32 - 2 * B : 64 - 8 * B; // drop symbols older than the block
-	prm.f1_words = (1u << fbits) / 32;
+	prm.f1_words = (uint32_t) (((uint64_t) 1 << fbits) / 32);
 	std::vector<uint32_t> bm(prm.f1_words, 0);
 	for (uint32_t j = 0; j < pd; j++)
 		for (uint32_t r = 0; r < s; r++) {
@@ -463,15 +498,26 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 	c.front_entry_bytes = 4;
 	c.front.resize((size_t) prm.f1_words * 4);
 	memcpy(c.front.data(), bm.data(), c.front.size());
-	// offset masks: a candidate block only has to be probed at the offsets r some pattern holds it at
+	// offset masks: a candidate block only has to be probed at the offsets r some pattern holds it at;
+	// in shared memory while 2 entries per (pattern, offset) fit 32 KiB, else 8 per pair in L2
 	if (s > 1) {
-		uint32_t rbits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 2), 10), 15);
+		const uint32_t eb = s > 8 ? 2 : 1;
+		uint32_t rbits = std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 2), 10);
+		prm.r_in_smem = 1;
+		if (((uint64_t) eb << rbits) > 32 * 1024) {
+			if (opts.force_smem_tables)
+				rbits = eb == 2 ? 14 : 15;
+			else {
+				prm.r_in_smem = 0;
+				rbits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 4), 16), 24);
+			}
+		}
 		if (opts.force_r_bits)
 			rbits = std::min<uint32_t>(std::max<uint32_t>(opts.force_r_bits, 10), 16);
 		prm.r_mult = kMultR;
 		prm.r_sh = 32 - rbits;
 		prm.r_entries = 1u << rbits;
-		prm.r_entry_bytes = s > 8 ? 2 : 1;
+		prm.r_entry_bytes = eb;
 		c.rmask.assign((size_t) prm.r_entries * prm.r_entry_bytes, 0);
 		for (uint32_t j = 0; j < pd; j++)
 			for (uint32_t r = 0; r < s; r++) {
@@ -485,7 +531,7 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 			}
 	}
 	build_verify(ps, packed, opts, c);
-	c.info.table_in_smem = 1;
+	c.info.table_in_smem = plan.in_smem ? 1 : 0;
 	return ACWM_OK;
 }
 
@@ -523,7 +569,8 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 		return rc;
 	// tables are rounded up to 16 bytes each in shared memory
 	const uint32_t smem_tables16 = (out.info.table_in_smem ? (((uint32_t) out.front.size() + 15u) & ~15u) : 0)
-			+ (((uint32_t) out.rmask.size() + 15u) & ~15u) + (((uint32_t) out.filter2.size() * 4 + 15u) & ~15u);
+			+ (prm.r_in_smem ? (((uint32_t) out.rmask.size() + 15u) & ~15u) : 0)
+			+ (prm.f2_in_smem ? (((uint32_t) out.filter2.size() * 4 + 15u) & ~15u) : 0);
 	LaunchShape shape = shape_for_tables(smem_tables16, packed);
 	if (opts.force_threads || opts.force_stages) { // tuning / tests
 		LaunchShape want{opts.force_threads ? opts.force_threads / 32 : shape.warps,

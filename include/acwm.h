@@ -69,6 +69,8 @@ typedef struct acwm_options {
 	uint32_t force_stages;      /* ring depth of the per-warp TMA tile pipeline: 1..4 (tuning); 0 = auto */
 	uint32_t force_f2_bits;     /* log2 of the stage-2 bitmap size in bits, 13..19 (tuning); 0 = auto */
 	uint32_t force_r_bits;      /* log2 of the number of WM offset-mask entries, 10..16 (tuning); 0 = auto */
+	uint32_t force_smem_tables; /* 1 = never place a scan table in global memory (L2), whatever the set size */
+	uint32_t reserved;
 } acwm_options;
 
 /* What the builder chose; for reports and tests. */
@@ -206,7 +208,8 @@ typedef struct acwm_scan_params {
 	uint32_t n_entries;
 	uint32_t n_classes;     /* bytes path AC */
 	uint32_t r_mult, r_sh, r_entries, r_entry_bytes; /* WM offset masks: ridx = (block * mult) >> sh; 0 entries = none */
-	uint32_t reserved[4];
+	uint32_t r_in_smem, f2_in_smem; /* 1: the table is staged in shared memory, 0: read from global memory (L2-resident) */
+	uint32_t reserved[2];
 } acwm_scan_params;
 
 /* ------------------- reference-shaped shims (smatcher.h) ------------------- */

@@ -24,14 +24,13 @@ def V(t, st, **kw):
     return d
 
 variants = {  # workload -> list of option dicts ({} = what the builder picks)
-    "c2": [{}, V(1024, 1, force_f2_bits=17, force_r_bits=14), V(1024, 1, force_f2_bits=16, force_r_bits=14),
-           V(768, 1), V(768, 1, force_f2_bits=17, force_r_bits=14), V(512, 2), V(512, 1),
-           V(768, 1, force_stride=4), V(1024, 1, force_stride=4, force_f2_bits=16)],
-    "c1": [{}, V(1024, 1), V(768, 1), V(512, 2), V(512, 1), V(768, 1, force_stride=2)],
-    "c2ac": [{}, V(512, 1), V(256, 2)],
-    "c1wm": [{}, V(768, 1), V(512, 2)],
-    "c3wm": [{}],
-    "c4": [{}, V(512, 2), V(384, 2), V(384, 3)],
+    "c2": [{}, V(768, 1), V(512, 1)],
+    "c1": [{}, V(768, 1), V(512, 1)],
+    "c2ac": [{}],
+    "c1wm": [{}],
+    "c3": [{}],
+    "c3wm": [{}, dict(force_smem_tables=1), V(768, 1), V(512, 1), dict(force_stride=8)],
+    "c4": [{}, dict(force_smem_tables=1), V(384, 2), V(256, 2), dict(force_stride=2)],
 }
 log("workload,text_mib,opts,stride,depth,exact,threads,smem,scan_us,finalize_us,GBps,frac_measured,count")
 texts = {}
@@ -67,5 +66,5 @@ for wl in wls:
             scan = float(np.median(ss)); fin = float(np.median(ff))
             gbps = (mib << 20) / scan / 1e9
             log(wl, mib, json.dumps(opts).replace(",", ";"), inf["stride"], inf["depth"], inf["exact_front"], f'{inf["threads"]}x{inf["stages"]}',
-                inf["smem_bytes"], f"{scan*1e6:.1f}", f"{fin*1e6:.1f}", f"{gbps:.1f}", f"{gbps/6543.1:.3f}", cnt)
+                f'{inf["smem_bytes"]}/l2={1 - inf["table_in_smem"]}', f"{scan*1e6:.1f}", f"{fin*1e6:.1f}", f"{gbps:.1f}", f"{gbps/6543.1:.3f}", cnt)
             mt.close()

@@ -43,6 +43,14 @@ RANDOM_CASES = [
     ("wm_english_p100_m3", WM, 128, 100, 3, 100_000, {}),
     ("wm_dna_bytes_path", WM, 4, 100, 8, 100_000, dict(force_bytes_path=1)),
     ("c4_wm_ascii_mixed_8_64", WM, 256, 2000, (8, 64), 200_000, {}),
+    # large sets: stage-1 bitmap / offset masks / stage-2 bitmap in global memory (L2-resident)
+    ("c3_wm_dna_p100000_m32_l2", WM, 4, 100000, 32, 200_000, {}),
+    ("wm_dna_p10000_m16_l2", WM, 4, 10000, 16, 200_000, {}),
+    ("wm_dna_p10000_m16_smem_only", WM, 4, 10000, 16, 100_000, dict(force_smem_tables=1)),
+    ("c4_wm_ascii_p10000_mixed_l2", WM, 256, 10000, (8, 64), 200_000, {}),
+    ("wm_ascii_p10000_m12_smem_only", WM, 256, 10000, 12, 100_000, dict(force_smem_tables=1)),
+    ("c3_ac_dna_p100000_m32", AC, 4, 100000, 32, 60_000, {}),
+    ("ac_dna_p10000_m16_f2_l2", AC, 4, 10000, 16, 100_000, {}),
 ]
 
 
