@@ -36,6 +36,7 @@ WORKLOADS = {
     "c1wm": ("WM", 4, 100, 8, "Wu-Manber on the configs[0] pattern set (100 patterns m=8)"),
     "c3": ("AC", 4, 100000, 32, "BASELINE configs[2] per-GPU shard: Aho-Corasick, DNA, 100000 patterns m=32"),
     "c3wm": ("WM", 4, 100000, 32, "Wu-Manber on the configs[2] pattern set"),
+    "ac10k16": ("AC", 4, 10000, 16, "Aho-Corasick, DNA, 10000 patterns m=16 (sweep point)"),
     "c4": ("WM", 256, 10000, (8, 64), "BASELINE configs[3]: Wu-Manber, 256-symbol text, 10000 patterns m=8..64"),
 }
 TEXT_SEED, PAT_SEED = 1, 2

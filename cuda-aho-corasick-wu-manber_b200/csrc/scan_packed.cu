@@ -67,15 +67,17 @@ struct PackedKey {
 // The lane's strides are laid out so that they END at the chunk end: in-chunk strides
 // start kOff symbols in front of the chunk (kOff = 2 for K = 3, since 112 = 3*37 + 1),
 // preceded by the warm-up strides that bring the state up to date.
-template <int K, bool EXACT>
+// GLOBAL: the automaton lives in global memory (L2-resident), uint32 entries, K <= 2.
+template <int K, bool EXACT, bool GLOBAL = false>
 struct FrontAC : PackedKey {
+	static constexpr int kSS = GLOBAL ? 2 : 1;                  // log2(entry bytes): symbols sit above it in the address
 	static constexpr int kOff = (K - (int) kLane % K) % K;      // 2 / 0 / 0
 	static constexpr int kStrides = ((int) kLane + kOff) / K;   // 38 / 56 / 112
 	static constexpr int kGroup = (K == 3) ? 10 : 32 / K;       // strides per hit word
 	static constexpr int kGroupSyms = kGroup * K;               // 30 / 32 / 32
 	static constexpr int kWords = (kStrides + kGroup - 1) / kGroup; // 4
-	static constexpr uint32_t kSymMask2 = ((1u << (2 * K)) - 1) << 1;
-	static constexpr uint32_t kRowMask = ~((1u << (2 * K + 1)) - 1);
+	static constexpr uint32_t kSymMask2 = ((1u << (2 * K)) - 1) << kSS;
+	static constexpr uint32_t kRowMask = ~((1u << (2 * K + kSS)) - 1);
 	static constexpr uint32_t kHitMask = (1u << K) - 1;
 	static constexpr int kExpand = 1; // probes per candidate
 
@@ -87,7 +89,7 @@ struct FrontAC : PackedKey {
 	uint32_t hw[kWords];
 
 	__device__ __forceinline__ void init(const uint8_t *table, const uint8_t *, const ScanArgs &a) {
-		tab = table;
+		tab = GLOBAL ? a.front : table;
 		// the state must have seen depth-1 symbols of history when the chunk starts; the first
 		// in-chunk stride covers kOff of them
 		const uint32_t need = a.prm.depth - 1;
@@ -101,7 +103,10 @@ struct FrontAC : PackedKey {
 
 	__device__ __forceinline__ uint32_t step(uint32_t sym2) {
 		const uint32_t addr = (ent & kRowMask) | sym2; // one LOP3 between two dependent lookups
-		ent = *reinterpret_cast<const uint16_t *>(tab + addr);
+		if (GLOBAL)
+			ent = __ldg(reinterpret_cast<const uint32_t *>(tab + addr));
+		else
+			ent = *reinterpret_cast<const uint16_t *>(tab + addr);
 		return ent & kHitMask;
 	}
 
@@ -125,7 +130,7 @@ struct FrontAC : PackedKey {
 			if (hist <= 16) {
 				uint32_t h = W[0] >> (32 - 2 * hist);
 				for (uint32_t i = 0; i < nwu; i++) {
-					(void) step((h << 1) & kSymMask2);
+					(void) step((h << kSS) & kSymMask2);
 					h >>= 2 * K;
 				}
 			} else {
@@ -139,7 +144,7 @@ struct FrontAC : PackedKey {
 					hi >>= sh;
 				}
 				for (uint32_t i = 0; i < nwu; i++) {
-					(void) step(((uint32_t) lo << 1) & kSymMask2);
+					(void) step(((uint32_t) lo << kSS) & kSymMask2);
 					lo = (lo >> (2 * K)) | (hi << (64 - 2 * K));
 					hi >>= 2 * K;
 				}
@@ -151,8 +156,8 @@ struct FrontAC : PackedKey {
 			const int wi = bit >> 5, sh = bit & 31;
 			uint32_t sym2;
 			if (sh + 2 * K <= 32)
-				sym2 = (sh >= 1 ? (W[wi] >> (sh - 1)) : (W[wi] << 1)) & kSymMask2;
-			else
+				sym2 = (sh >= kSS ? (W[wi] >> (sh >= kSS ? sh - kSS : 0)) : (W[wi] << (sh < kSS ? kSS - sh : 0))) & kSymMask2;
+			else // only K = 3 straddles words, and K = 3 tables are never global
 				sym2 = __funnelshift_r(W[wi], W[wi + 1], sh - 1) & kSymMask2;
 			uint32_t h = step(sym2);
 			if (i == 0 && kOff)
@@ -253,6 +258,15 @@ cudaError_t launch_scan_packed(const ScanArgs &a, uint32_t threads, uint32_t sme
 	const acwm_scan_params &p = a.prm;
 	if (p.algo == ACWM_ALGO_AC) {
 		const bool ex = p.exact_front != 0;
+		if (!a.front_in_smem) {
+			if (p.stride == 2)
+				return ex ? launch_front<FrontAC<2, true, true>, true>(a, threads, smem, grid, st)
+						  : launch_front<FrontAC<2, false, true>, false>(a, threads, smem, grid, st);
+			if (p.stride == 1)
+				return ex ? launch_front<FrontAC<1, true, true>, true>(a, threads, smem, grid, st)
+						  : launch_front<FrontAC<1, false, true>, false>(a, threads, smem, grid, st);
+			return cudaErrorInvalidValue;
+		}
 		switch (p.stride) {
 		case 3: return ex ? launch_front<FrontAC<3, true>, true>(a, threads, smem, grid, st)
 						  : launch_front<FrontAC<3, false>, false>(a, threads, smem, grid, st);

@@ -109,7 +109,7 @@ static void build_verify(const PatternSet &ps, bool packed, const acwm_options &
 	// measured no faster (profiles/r01d_tune.csv) and every CTA has to load it
 	// shared memory up to 2^18 bits (32 KiB); larger sets get an L2-resident bitmap of up to 2^26 bits
 	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 64), 13),
-			opts.force_smem_tables ? 18 : 26);
+			(opts.force_smem_tables || pd <= 16384) ? 18 : 26);
 	if (opts.force_f2_bits)
 		f2bits = std::min<uint32_t>(std::max<uint32_t>(opts.force_f2_bits, 13), 26);
 	if (packed && key_bits <= f2bits) {
@@ -263,7 +263,8 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 	acwm_scan_params &prm = c.prm;
 	const uint32_t m = ps.m_min;
 	const uint32_t Dmax = std::min<uint32_t>(m, kMaxDepthPacked);
-	// cost model (lane-instructions per symbol): 7 per DFA lookup, ~25 per verified candidate
+	// cost model (lane-instruction slots per symbol): 7 per DFA lookup, ~100 per candidate (checked by its own
+	// lane while the rest of the warp waits)
 	double best_cost = 1e30;
 	uint32_t bestK = 0, bestD = 0;
 	uint32_t d_lo = 1, d_hi = Dmax;
@@ -285,7 +286,7 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 			const uint64_t bytes = (uint64_t) t.rows << (2 * K + 1);
 			if (bytes > budget || bytes >= 65536)
 				continue;
-			const double cost = 7.0 / K + rate * 25.0;
+			const double cost = 7.0 / K + rate * 100.0;
 			if (cost < best_cost - 1e-9) {
 				best_cost = cost;
 				bestK = K;
@@ -293,19 +294,47 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 			}
 		}
 	}
+	// When no automaton that fits shared memory filters well (large sets: every short suffix occurs), the
+	// automaton goes to global memory: uint32 entries, K <= 2, served from L2 (access-policy window).
+	// One dependent L2 lookup per K symbols (~40 slots) against a candidate rate that drops 4x per level.
+	bool global = false;
+	const uint64_t kGlobalBytesMax = 48ull << 20;
+	if (!opts.force_smem_tables && (best_cost > 12.0 || !bestK)) {
+		for (uint32_t D = std::min<uint32_t>(d_hi, 16); D >= std::max<uint32_t>(d_lo, 2); D--) {
+			Trie t;
+			build_suffix_trie(ps, D, 4, nullptr, (uint32_t) (kGlobalBytesMax / 16), t);
+			if (t.overflow)
+				continue;
+			const bool exact = (D == m);
+			const double rate = exact ? 0.0 : std::min(1.0, (double) t.leaves / std::pow(4.0, (double) D));
+			for (uint32_t K = 2; K >= 1; K--) {
+				if (opts.force_stride && opts.force_stride != K)
+					continue;
+				if (((uint64_t) t.rows << (2 * K + 2)) > kGlobalBytesMax)
+					continue;
+				const double cost = 40.0 / K + rate * 100.0;
+				if (cost < best_cost - 1e-9) {
+					best_cost = cost;
+					bestK = K;
+					bestD = D;
+					global = true;
+				}
+			}
+		}
+	}
 	if (!bestK) {
-		err = "AC: no (stride, depth) fits the shared-memory table budget";
+		err = "AC: no (stride, depth) fits the table budget";
 		return ACWM_ERR_UNSUPPORTED;
 	}
 	Trie t;
-	build_suffix_trie(ps, bestD, 4, nullptr, max_rows_any, t);
+	build_suffix_trie(ps, bestD, 4, nullptr, global ? (uint32_t) (kGlobalBytesMax / 16) : max_rows_any, t);
 	std::vector<uint32_t> next1;
 	uint32_t n_rows = 0;
 	build_dfa1(t, next1, n_rows);
 	const uint32_t K = bestK, cols = 1u << (2 * K);
-	c.front_entry_bytes = 2;
-	c.front.assign((size_t) n_rows * cols * 2, 0);
-	uint16_t *tab = reinterpret_cast<uint16_t *>(c.front.data());
+	const uint32_t eb = global ? 4 : 2; // entry = byte offset of the next row | hit bits
+	c.front_entry_bytes = eb;
+	c.front.assign((size_t) n_rows * cols * eb, 0);
 	for (uint32_t r = 0; r < n_rows; r++)
 		for (uint32_t idx = 0; idx < cols; idx++) {
 			uint32_t st = r, hits = 0;
@@ -314,7 +343,11 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 				hits |= (e & 1) << i;
 				st = e >> 1;
 			}
-			tab[(size_t) r * cols + idx] = (uint16_t) ((st << (2 * K + 1)) | hits);
+			if (global)
+				reinterpret_cast<uint32_t *>(c.front.data())[(size_t) r * cols + idx] = (st * cols * 4) | hits;
+			else
+				reinterpret_cast<uint16_t *>(c.front.data())[(size_t) r * cols + idx] =
+						(uint16_t) ((st << (2 * K + 1)) | hits);
 		}
 	prm.stride = K;
 	prm.depth = bestD;
@@ -322,7 +355,7 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 	prm.n_rows = n_rows;
 	if (!prm.exact_front)
 		build_verify(ps, true, opts, c);
-	c.info.table_in_smem = 1;
+	c.info.table_in_smem = global ? 0 : 1;
 	return ACWM_OK;
 }
 
@@ -425,8 +458,9 @@ static WmPlan plan_wm_stride(const PatternSet &ps, bool packed, uint32_t s, uint
 		// warp waits) plus ~40 per offset it has to probe: about `load` offsets, at most s
 		const double load = entries / std::pow(2.0, (double) std::min(fbits, key_bits));
 		const double rate = 1.0 - std::exp(-load);
-		// per symbol: ~8 lane-instructions per sample (+4 when the bitmap word comes from L2)
-		const double cost = ((packed ? 8.0 : 10.0) + (in_smem ? 0.0 : 4.0) + rate * 60.0
+		// per symbol: ~8 lane-instructions per sample (+16 when the bitmap word comes from L2: measured on
+		// BASELINE config 4, profiles/r01g_tune.csv)
+		const double cost = ((packed ? 8.0 : 10.0) + (in_smem ? 0.0 : 16.0) + rate * 60.0
 									+ std::min<double>(s, load) * 40.0) / s;
 		if (cost < best.cost - 1e-9) {
 			best.s = s;
@@ -502,11 +536,13 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 	// in shared memory while 2 entries per (pattern, offset) fit 32 KiB, else 8 per pair in L2
 	if (s > 1) {
 		const uint32_t eb = s > 8 ? 2 : 1;
+		const uint32_t rbits_smem_max = eb == 2 ? 14 : 15; // 32 KiB
 		uint32_t rbits = std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 2), 10);
 		prm.r_in_smem = 1;
-		if (((uint64_t) eb << rbits) > 32 * 1024) {
-			if (opts.force_smem_tables)
-				rbits = eb == 2 ? 14 : 15;
+		if (rbits > rbits_smem_max) {
+			// shared memory while at most ~2 (pattern, offset) pairs share an entry, else L2
+			if (opts.force_smem_tables || (uint64_t) s * pd <= ((uint64_t) 2 << rbits_smem_max))
+				rbits = rbits_smem_max;
 			else {
 				prm.r_in_smem = 0;
 				rbits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 4), 16), 24);

@@ -28,7 +28,8 @@ variants = {  # workload -> list of option dicts ({} = what the builder picks)
     "c1": [{}, V(768, 1), V(512, 1)],
     "c2ac": [{}],
     "c1wm": [{}],
-    "c3": [{}],
+    "c3": [{}, dict(force_stride=1), dict(force_smem_tables=1)],
+    "ac10k16": [{}, dict(force_smem_tables=1)],
     "c3wm": [{}, dict(force_smem_tables=1), V(768, 1), V(512, 1), dict(force_stride=8)],
     "c4": [{}, dict(force_smem_tables=1), V(384, 2), V(256, 2), dict(force_stride=2)],
 }

@@ -151,7 +151,9 @@ class Emulator:
             sym = text.astype(np.int64)
             win = self._win16(text)
             if p.algo == acwm.AC:
-                hits = self._ac_hits(sym, 112, 2, 1 << (2 * p.stride), 2 * p.stride + 1)  # entry = row byte offset | hits
+                # entry = byte offset of the next row | hits (uint16 in shared memory, uint32 in global memory)
+                hits = self._ac_hits(sym, 112, 2, 1 << (2 * p.stride),
+                                     2 * p.stride + (1 if self.info["table_in_smem"] else 2))
                 hits = hits[(hits >= m_min - 1) & (hits < n)]
                 if p.exact_front:
                     return int(hits.size), hits.astype(np.uint64)
