@@ -198,7 +198,7 @@ def run_ours(args):
     text0 = dg.text_host(n, alphabet, TEXT_SEED)
     pats, m_max = make_patterns(dg, text0, args.workload)
     halo = m_max - 1
-    mt = acwm.Matcher(algo, pats, alphabet)
+    mt = acwm.Matcher(algo, pats, alphabet, **json.loads(args.matcher_opts))
     pos_cap = max(1 << 20, n // 16)
     mt.upload(local_rank, pos_cap)
 
@@ -241,6 +241,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    mt.set_overlap(not args.no_overlap)  # consecutive scans of resident texts: programmatic dependent launches
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -264,6 +265,7 @@ def run_ours(args):
     value = world * text_bytes / (ms_per_step * 1e-3) / 1e9
 
     # ---- results of the last step (parity of the global count is a test, here it is reported)
+    mt.set_overlap(False)
     last_count, last_pos, _ = mt.fetch(cap=pos_cap, stream=stream)
     global_count = sh.allreduce_count(last_count, dev)
     if fused_exchange:  # what the kernels exchanged must be what NCCL sums
@@ -344,7 +346,9 @@ def run_ours(args):
                        "count_exchange": ("none (1 GPU)" if world == 1 else
                                           "in-kernel st.release.sys into NVLink peer mailboxes (torch symmetric memory)"
                                           if fused_exchange else "NCCL all_reduce of the 8-byte count per step"),
-                       "launch": "one cooperative kernel per step (scan + position ordering + result), no memset / finalize nodes",
+                       "launch": "one kernel per step (scan + position ordering + result), no memset / finalize nodes; "
+                                 + ("cooperative launches" if args.no_overlap else
+                                    "consecutive steps chained as programmatic dependent launches (acwm_set_overlap)"),
                        "kernel": {k: info[k] for k in ("packed2bit", "stride", "depth", "exact_front", "n_rows",
                                                         "table_in_smem", "smem_bytes", "threads", "stages")}},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": e2e_bytes,
@@ -417,6 +421,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--text-mib", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="plain cooperative launches in the timed loop")
+    ap.add_argument("--matcher-opts", default="{}", help="JSON of acwm_options overrides (tuning experiments)")
     ap.add_argument("--nccl-count", action="store_true", help="all-reduce the count with NCCL instead of in-kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -88,6 +88,7 @@ def lib():
         L.acwm_last_kernel_seconds.restype = C.c_double
         L.acwm_last_kernel_seconds.argtypes = [C.c_void_p]
         L.acwm_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.acwm_set_overlap.argtypes = [C.c_void_p, C.c_int]
         L.acwm_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, _u64p]
         L.acwm_fetch_global_count.argtypes = [C.c_void_p, _u64p, C.c_void_p]
         L.acwm_profiled_seconds.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -222,6 +223,10 @@ class Matcher:
                     allow=(ERR_OVERFLOW,) if allow_overflow else ())
         self.last_rc = rc
         return int(count.value), pos[:int(nw.value)]
+
+    def set_overlap(self, on: bool):
+        """Back-to-back device scans may overlap (programmatic dependent launch); see acwm_set_overlap."""
+        _check(lib().acwm_set_overlap(self._h, int(on)))
 
     def set_peers(self, rank: int, world: int, mailbox_ptrs):
         """In-kernel count exchange over peer memory (see acwm_set_peers); None / world<=1 = off."""

@@ -183,6 +183,7 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.epoch = mt->epoch++;
 	a.want_positions = want_positions;
 	a.append = append;
+	a.pdl = (exchange && mt->overlap) ? 1 : 0; // device-resident scans only (exchange == "called from acwm_scan_device")
 	if (exchange && mt->peer_world > 1) {
 		a.world = mt->peer_world;
 		a.rank = mt->peer_rank;
@@ -385,6 +386,13 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 }
 
 double acwm_last_kernel_seconds(const acwm_matcher *mt) { return mt ? mt->last_kernel_s : 0.0; }
+
+int acwm_set_overlap(acwm_matcher *mt, int on) {
+	if (!mt)
+		return set_error(ACWM_ERR_INVALID, "matcher == NULL");
+	mt->overlap = on != 0;
+	return ACWM_OK;
+}
 
 int acwm_set_peers(acwm_matcher *mt, uint32_t rank, uint32_t world, const uint64_t *mailboxes) {
 	if (!mt)

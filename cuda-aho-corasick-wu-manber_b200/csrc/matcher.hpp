@@ -51,6 +51,7 @@ struct acwm_matcher {
 	std::vector<cudaEvent_t> ev_time;
 	std::array<cudaEvent_t, 2> ev_prof{};
 	bool profiling = false;
+	bool overlap = false;
 	uint32_t epoch = 0;
 	// multi-GPU count exchange (acwm_set_peers)
 	uint32_t peer_world = 0, peer_rank = 0, xepoch = 0;

@@ -64,7 +64,8 @@ struct ScanArgs {
 	uint32_t world, rank, xepoch;
 	unsigned long long *peers[kMaxPeers];
 	int want_positions;
-	int append;                  // 1: add to ctl->result instead of replacing it (chunked host text)
+	int append;
+	int pdl;                     // 1: launched as a programmatic dependent launch (consecutive scans may overlap)                  // 1: add to ctl->result instead of replacing it (chunked host text)
 };
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -161,6 +162,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
+
+// programmatic dependent launch: wait for the previous kernel of the stream / let the next one become resident
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Warp-level staging of the matches of one tile.  A warp reserves staging slots in blocks
 // (one atomic per >= kStageBlock matches instead of one per tile) and leaves the unused

@@ -15,6 +15,9 @@
 //               the CTA's match count; the last CTA to arrive writes the result block.  The
 //               working counters are double-buffered by launch parity, each launch clears its
 //               successor's copy (no memset node between scans).
+// Overlap mode (acwm_set_overlap): the launch is a programmatic dependent launch -- its prologue and its
+// read-only scan phase start while the previous scan of the stream retires (griddepcontrol), and wait
+// for that scan to complete right before their first write to the scratch arrays.
 //   4. exchange (multi-GPU) the publishing thread stores the rank's count into every peer's mailbox
 //               over NVLink (system-scope stores on peer-mapped memory) and, at its very end, sums
 //               what the peers left in its own mailbox for the PREVIOUS scan: an all-reduce of the
@@ -97,6 +100,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		pk[kPackWords - 3 + lane] = 0;
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncthreads();
+	if (a.pdl)
+		pdl_trigger(); // overlap mode: the next scan of the stream may take over SMs as our CTAs retire
 
 	// tables: global -> shared with TMA bulk copies, overlapped with the first text tiles
 	const uint32_t tab_bytes = front_smem + rm_bytes + f2_bytes;
@@ -167,6 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	const uint32_t *f2 = a.prm.f2_in_smem ? s_f2 : a.filter2;
 	fr.init(s_front, a.prm.r_in_smem ? s_rmask : a.rmask, a);
 
+	bool waited = false;
 	for (uint32_t slot = 0;; slot = slot + 1 == stages ? 0 : slot + 1) {
 		const uint32_t idx = s_tid[slot];
 		if (idx >= n_b)
@@ -188,6 +194,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 
 		em.tile = tile;
 		em.idx = idx;
+		// overlap mode: up to here the warp has only read (text, tables); the previous scan of the stream may
+		// still be ordering its matches in the scratch arrays we are about to write
+		if (a.pdl && !waited && (idx >= a.cnt_cap || __any_sync(kFull, fr.count() != 0))) {
+			pdl_wait();
+			waited = true;
+		}
 		const uint64_t tile_start = tile * (uint64_t) kTile;
 		uint32_t total = 0;
 		if constexpr (EXACT) {
@@ -306,6 +318,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		if constexpr (!kPacked)
 			refill(slot);
 	}
+	if (a.pdl && !waited)
+		pdl_wait(); // the previous scan is complete: the scratch arrays and the control block are ours now
 	em.finish();
 
 	// ---- per-CTA totals (shared memory)
@@ -489,9 +503,18 @@ static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid,
 	cfg.blockDim = dim3(THREADS);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = st;
+	// The grid barrier needs every CTA resident: grid <= #SMs at one CTA per SM, and the launch is cooperative
+	// so that the runtime checks it.  Overlap mode trades that check for a programmatic dependent launch (the
+	// two attributes together serialise, profiles/README.md session i): the grid is the same, so the CTAs
+	// still all become resident as the previous scan's CTAs retire.
 	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeCooperative; // the grid barrier needs every CTA resident
-	attr[0].val.cooperative = 1;
+	if (a.pdl) {
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+	} else {
+		attr[0].id = cudaLaunchAttributeCooperative;
+		attr[0].val.cooperative = 1;
+	}
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
 	return cudaLaunchKernelEx(&cfg, kern, a);

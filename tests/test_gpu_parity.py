@@ -114,6 +114,34 @@ def test_device_resident_unaligned_and_report_from(acwm, oracle, torch_cuda):
         mt.close()
 
 
+def test_overlapped_back_to_back_scans(acwm, oracle, torch_cuda):
+    """acwm_set_overlap: consecutive scans chained as programmatic dependent launches (the next scan's
+    read-only phase runs while the previous one orders its matches) still give the oracle's result."""
+    torch = torch_cuda
+    dg = __import__("acwm_pkg").submodule("datagen")
+    for cname in ("c1_ac_dna_p100_m8", "c2_wm_dna_p1000_m16", "wm_ascii_p1000_m8", "ac_dna_depth5"):
+        case = next(c for c in RANDOM_CASES if c[0] == cname)
+        name, algo, alphabet, p, m, n, opts = case
+        pats, text = make_case(case)
+        big = np.concatenate([text] * 24)  # ~6 MB: enough tiles for every CTA
+        other = dg.text_host(big.size - 12345, alphabet, 77)
+        other[1000:1000 + pats.shape[1]] = pats[0]
+        refs = [oracle.set_search(pats, t) for t in (big, other)]
+        d = [torch.from_numpy(t).cuda() for t in (big, other)]
+        mt = acwm.Matcher(algo, pats, alphabet, **opts).upload(pos_capacity=big.size)
+        mt.set_overlap(True)
+        st = torch.cuda.current_stream().cuda_stream
+        for rounds in (1, 2, 5):
+            for last in (0, 1):
+                for k in range(rounds):  # no synchronisation between the launches
+                    mt.scan_tensor(d[(last + k + 1) % 2], want_positions=bool(k & 1))
+                mt.scan_tensor(d[last])
+                count, pos, _ = mt.fetch(cap=big.size, stream=st)
+                assert count == refs[last]["count"], (cname, rounds, last)
+                assert np.array_equal(pos, refs[last]["positions"]), (cname, rounds, last)
+        mt.close()
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_sharded_scans_sum_to_whole(acwm, oracle, torch_cuda, world):
     """The multi-GPU geometry run on one GPU: shard scans are exactly-once."""
