@@ -256,10 +256,12 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = mt.launch_count - launches0
+    per_rank_ms = [elapsed_ms / args.steps]
     if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([elapsed_ms], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(g.item()) / args.steps for g in gathered]
+        elapsed_ms = max(per_rank_ms) * args.steps  # max over ranks
     ms_per_step = elapsed_ms / args.steps
     text_bytes = sum(int(dev_texts[(args.warmup + i) % N_ROTATE].numel()) for i in range(args.steps)) / args.steps
     value = world * text_bytes / (ms_per_step * 1e-3) / 1e9
@@ -365,6 +367,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "frac_of_8TBps_spec": achieved / 8000.0},
             "matches_last_step": int(global_count),
+            "per_rank_ms_per_step": [round(x, 5) for x in per_rank_ms],
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
