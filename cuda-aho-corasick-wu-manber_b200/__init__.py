@@ -100,6 +100,17 @@ def lib():
         L.acwm_shard_bounds.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u64p]
         L.acwm_shard_bounds.restype = None
         L.acwm_table_blob.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _u64p]
+        L.acwm_set_trace.argtypes = [C.c_void_p, C.c_void_p]
+        L.acwm_trace_words_per_cta.restype = C.c_uint32
+        L.acwm_symbol_map.argtypes = [C.c_uint32, _u8p]
+        L.acwm_encode_symbols.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, _u64p]
+        L.acwm_load_text.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), _u64p]
+        L.acwm_free_text.argtypes = [C.c_void_p]
+        L.acwm_free_text.restype = None
+        L.acwm_patterns_with_hits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
+                                              C.c_uint32, C.c_void_p]
+        L.acwm_select_data_file.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_char_p, C.c_char_p, C.c_char_p,
+                                            C.c_size_t]
         _lib = L
     return _lib
 
@@ -241,6 +252,10 @@ class Matcher:
         _check(lib().acwm_fetch_global_count(self._h, C.byref(g), C.c_void_p(stream)))
         return int(g.value)
 
+    def set_trace(self, d_trace_ptr: int | None):
+        """Kernel timeline instrumentation (see acwm_set_trace); None = off."""
+        _check(lib().acwm_set_trace(self._h, C.c_void_p(d_trace_ptr or 0)))
+
     def set_profiling(self, on: bool):
         _check(lib().acwm_set_profiling(self._h, int(on)))
 
@@ -257,3 +272,45 @@ class Matcher:
     @property
     def launch_count(self) -> int:
         return int(lib().acwm_launch_count(self._h))
+
+
+# ---------------------------------------------------------------- data files (main.c:31-123,453)
+def symbol_map(alphabet: int) -> np.ndarray:
+    m = np.zeros(256, np.uint8)
+    _check(lib().acwm_symbol_map(alphabet, m.ctypes.data_as(_u8p)))
+    return m
+
+
+def encode_symbols(raw, alphabet: int) -> np.ndarray:
+    """Corpus bytes -> symbol codes in [0, alphabet) (FASTA headers / non-symbols dropped)."""
+    raw = np.ascontiguousarray(np.frombuffer(raw, np.uint8) if isinstance(raw, (bytes, bytearray)) else raw, np.uint8)
+    out = np.empty(max(raw.size, 1), np.uint8)
+    n = C.c_uint64()
+    _check(lib().acwm_encode_symbols(C.c_void_p(raw.ctypes.data), raw.size, alphabet, C.c_void_p(out.ctypes.data),
+                                     C.byref(n)))
+    return out[:int(n.value)].copy()
+
+
+def load_text(path: str, alphabet: int, max_symbols: int = 0) -> np.ndarray:
+    ptr, n = C.c_void_p(), C.c_uint64()
+    _check(lib().acwm_load_text(os.fsencode(path), alphabet, max_symbols, C.byref(ptr), C.byref(n)))
+    try:
+        buf = (C.c_uint8 * max(int(n.value), 1)).from_address(ptr.value)
+        return np.frombuffer(buf, np.uint8)[:int(n.value)].copy()
+    finally:
+        lib().acwm_free_text(ptr)
+
+
+def patterns_with_hits(text: np.ndarray, m: int, p: int, alphabet: int, seed: int, hit_percent: int = 50) -> np.ndarray:
+    text = np.ascontiguousarray(text, np.uint8)
+    out = np.empty((p, m), np.uint8)
+    _check(lib().acwm_patterns_with_hits(C.c_void_p(text.ctypes.data), text.size, m, p, alphabet, seed, hit_percent,
+                                         C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def select_data_file(m: int, n: int, alphabet: int, data_root: str | None = None):
+    """(pattern_path, text_path) of main.c:31-123; raises AcwmError for the reference's fail() cases."""
+    pp, tp = C.create_string_buffer(4096), C.create_string_buffer(4096)
+    _check(lib().acwm_select_data_file(m, n, alphabet, os.fsencode(data_root) if data_root else None, pp, tp, 4096))
+    return os.fsdecode(pp.value), os.fsdecode(tp.value)

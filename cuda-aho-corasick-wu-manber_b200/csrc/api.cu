@@ -149,6 +149,16 @@ static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
 	mt->l2_window_stream = (void *) st; // set once per stream, not once per scan
 }
 
+// Kernel variants that can be switched off for A/B measurements (scripts/tune.py): ACWM_TUNE = OR of
+// 1 (warp-cooperative candidate verification) and 2 (CTAs of a sparse scan retire without the grid wait).
+static uint32_t kernel_tune() {
+	static const uint32_t v = [] {
+		const char *e = getenv("ACWM_TUNE");
+		return e && *e ? (uint32_t) strtoul(e, nullptr, 0) : (kTuneCoopVerify | kTuneEarlyRetire);
+	}();
+	return v;
+}
+
 // Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
 // cooperative kernel that scans, orders the positions and publishes the result block.
 static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
@@ -184,6 +194,8 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.want_positions = want_positions;
 	a.append = append;
 	a.pdl = (exchange && mt->overlap) ? 1 : 0; // device-resident scans only (exchange == "called from acwm_scan_device")
+	a.tune = kernel_tune();
+	a.trace = mt->d_trace;
 	if (exchange && mt->peer_world > 1) {
 		a.world = mt->peer_world;
 		a.rank = mt->peer_rank;
@@ -429,6 +441,15 @@ int acwm_fetch_global_count(acwm_matcher *mt, uint64_t *global_count, void *stre
 	*global_count = mt->h_res->global_count;
 	return ACWM_OK;
 }
+
+int acwm_set_trace(acwm_matcher *mt, unsigned long long *d_trace) {
+	if (!mt)
+		return set_error(ACWM_ERR_INVALID, "matcher == NULL");
+	mt->d_trace = d_trace;
+	return ACWM_OK;
+}
+
+uint32_t acwm_trace_words_per_cta(void) { return kTraceWords; }
 
 int acwm_set_profiling(acwm_matcher *mt, int on) {
 	if (!mt)

@@ -52,6 +52,7 @@ struct acwm_matcher {
 	std::array<cudaEvent_t, 2> ev_prof{};
 	bool profiling = false;
 	bool overlap = false;
+	unsigned long long *d_trace = nullptr; // acwm_set_trace (caller-owned device buffer)
 	uint32_t epoch = 0;
 	// multi-GPU count exchange (acwm_set_peers)
 	uint32_t peer_world = 0, peer_rank = 0, xepoch = 0;

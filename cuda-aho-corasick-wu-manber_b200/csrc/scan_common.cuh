@@ -23,12 +23,21 @@ struct Result {
 // clears work[(k + 1) & 1] for its successor (which starts only after k is done), so no
 // memset node is needed between scans.
 struct Work {
-	unsigned long long arrive;   // [CTAs arrived : 16 | matches : 48] -- one atomic per CTA is count, grid barrier and exit ticket
+	unsigned long long arrive;   // [CTAs arrived : 9 | of which order the positions : 9 | matches : 46] -- one atomic per CTA is
+	                             // count, grid barrier, exit ticket and the CTA's slot in the ordering epilogue
 	unsigned long long cursor;   // staging slots handed out
 	unsigned int bad_text;
 	unsigned int pad[3];
 };
-constexpr unsigned kArriveShift = 48;
+constexpr unsigned kArriveShift = 55, kStayShift = 46; // grids of up to 256 CTAs
+constexpr unsigned long long kArriveCountMask = (1ull << kStayShift) - 1;
+constexpr unsigned kMailShift = 48;   // mailbox word of the count exchange: [epoch tag : 16 | count : 48]
+// A CTA that arrives while at most this many staging slots are handed out does not wait for the grid: it retires
+// (the next scan of the stream takes over its SM) and leaves the ordering to the CTAs that arrive after the
+// staging cursor has passed the mark -- or, when none has, to the last CTA to arrive, alone.
+constexpr unsigned long long kSoloStage = 4096;
+// ScanArgs.tune bits
+constexpr uint32_t kTuneCoopVerify = 1u, kTuneEarlyRetire = 2u;
 
 struct Control {
 	Result result;
@@ -64,8 +73,10 @@ struct ScanArgs {
 	uint32_t world, rank, xepoch;
 	unsigned long long *peers[kMaxPeers];
 	int want_positions;
-	int append;
-	int pdl;                     // 1: launched as a programmatic dependent launch (consecutive scans may overlap)                  // 1: add to ctl->result instead of replacing it (chunked host text)
+	int append;                  // 1: add to ctl->result instead of replacing it (chunked host text)
+	int pdl;                     // 1: launched as a programmatic dependent launch (consecutive scans may overlap)
+	uint32_t tune;               // kTune* bits
+	unsigned long long *trace;   // instrumentation (acwm_set_trace): kTraceWords of %globaltimer stamps per CTA, else NULL
 };
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -85,9 +96,9 @@ __device__ __forceinline__ unsigned long long collect_mailbox(const unsigned lon
 	const unsigned long long *slot = box + (x & (kPeerRing - 1)) * world;
 	for (uint32_t r = 0; r < world; r++) {
 		unsigned long long v;
-		while (((v = ld_relaxed_sys_u64(slot + r)) >> 48) != (x & 0xffffu))
+		while (((v = ld_relaxed_sys_u64(slot + r)) >> kMailShift) != (x & 0xffffu))
 			__nanosleep(32);
-		sum += v & ((1ull << 48) - 1);
+		sum += v & ((1ull << kMailShift) - 1);
 	}
 	return sum;
 }
@@ -161,6 +172,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 	unsigned long long v;
 	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
+}
+
+// instrumentation: phase time stamps of every CTA (scripts/trace.py turns them into a timeline)
+constexpr uint32_t kTraceWords = 16 + 3 * 32; // [16 CTA phases][32 warps: first tile ready][32: scan loop done][32: tiles scanned]
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__device__ __forceinline__ void trace_mark(const ScanArgs &a, uint32_t slot) {
+	if (a.trace)
+		a.trace[(size_t) blockIdx.x * kTraceWords + slot] = globaltimer_ns();
 }
 
 // programmatic dependent launch: wait for the previous kernel of the stream / let the next one become resident

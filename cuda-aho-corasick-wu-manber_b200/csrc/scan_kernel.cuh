@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_warps + W * warp_smem_bytes(stages, kPacked)); // a.cnt_cap words
 
 	if (threadIdx.x == 0) {
+		trace_mark(a, 0);
 		mbar_init(tab_bar, 1);
 		*s_next = 0;
 		*s_bad = 0;
@@ -100,6 +101,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		pk[kPackWords - 3 + lane] = 0;
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncthreads();
+	if (threadIdx.x == 0)
+		trace_mark(a, 1);
 	if (a.pdl)
 		pdl_trigger(); // overlap mode: the next scan of the stream may take over SMs as our CTAs retire
 
@@ -154,6 +157,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	for (uint32_t s = 0; s < stages; s++)
 		refill(s);
 	__syncwarp();
+	if (threadIdx.x == 0)
+		trace_mark(a, 2);
+	uint32_t n_scanned = 0;
 
 	uint32_t badacc = 0;
 	Work *wk = &a.ctl->work[a.epoch & 1u];
@@ -167,12 +173,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	em.blk_ptr = em.old_ptr = em.new_ptr = 0;
 	em.blk_left = em.old_left = 0;
 	Front fr;
-	if (tab_bytes)
-		mbar_wait(tab_bar, 0);
 	const uint32_t *f2 = a.prm.f2_in_smem ? s_f2 : a.filter2;
 	fr.init(s_front, a.prm.r_in_smem ? s_rmask : a.rmask, a);
 
 	bool waited = false;
+	bool tab_ready = tab_bytes == 0; // the tables are first needed by walk(): the first tile is loaded and packed under their copy
 	for (uint32_t slot = 0;; slot = slot + 1 == stages ? 0 : slot + 1) {
 		const uint32_t idx = s_tid[slot];
 		if (idx >= n_b)
@@ -190,7 +195,16 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			__syncwarp();
 			refill(slot);
 		}
+		if (!tab_ready) {
+			if (lane == 0)
+				trace_mark(a, 16 + warp); // first tile in registers
+			mbar_wait(tab_bar, 0);
+			tab_ready = true;
+			if (threadIdx.x == 0)
+				trace_mark(a, 3);
+		}
 		fr.walk(a);
+		n_scanned++;
 
 		em.tile = tile;
 		em.idx = idx;
@@ -237,34 +251,91 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		} else {
 			if constexpr (kPacked)
 				__syncwarp(); // the 2-bit copy of the tile (pk) is complete
-			// every lane checks its own candidates: offset mask -> stage-2 bitmap -> buckets;
-			// survivors become bits of mw (chunk-relative end positions)
+			// candidates -> offset mask -> stage-2 bitmap -> buckets; survivors become bits of mw (chunk-relative
+			// end positions) of the lane that owns the chunk
 			uint32_t mw0 = 0, mw1 = 0, mw2 = 0, mw3 = 0, multi = 0;
+			auto set_mw = [&](uint32_t p) {
+				const uint32_t bit = 1u << (p & 31);
+				if (p < 32)
+					mw0 |= bit;
+				else if (p < 64)
+					mw1 |= bit;
+				else if (p < 96)
+					mw2 |= bit;
+				else
+					mw3 |= bit;
+			};
+			// how many distinct patterns end at tile symbol tp (0: none)
+			auto check_end = [&](uint32_t tp) -> uint32_t {
+				const uint32_t key = Front::key_at(a, buf, pk, tp);
+				const uint32_t i2 = (uint32_t) (key * a.prm.f2_mult) >> a.prm.f2_sh;
+				if ((f2[i2 >> 5] >> (i2 & 31)) & 1u)
+					return verify_window(a, key, tile_start + tp);
+				return 0u;
+			};
+			const uint32_t ncand = fr.count();
+			const uint32_t tot_c = __reduce_add_sync(kFull, ncand);
+			if (tot_c == 0) {
+				// the usual tile of a selective filter
+			} else if ((a.tune & kTuneCoopVerify) && tot_c <= kListCap) {
+				// few candidates, unevenly spread over the lanes: compact them into the warp's list and let
+				// lane i check candidate i (one pass instead of max-per-lane divergent iterations)
+				uint32_t k = warp_incl_scan(ncand) - ncand;
 #pragma unroll
-			for (int g = 0; g < Front::kWords; g++) {
-				uint32_t w = fr.hw[g];
-				while (w) {
-					const int b = __ffs(w) - 1;
-					w &= w - 1;
-					const uint32_t c = Front::sym_of(g, b);
-					uint32_t rm = fr.probe_mask(a, buf, pk, lane * kLane + c);
-					while (rm) {
-						const uint32_t p = c + (uint32_t) (__ffs(rm) - 1);
-						rm &= rm - 1;
-						const uint32_t key = Front::key_at(a, buf, pk, lane * kLane + p);
-						const uint32_t i2 = (uint32_t) (key * a.prm.f2_mult) >> a.prm.f2_sh;
-						if ((f2[i2 >> 5] >> (i2 & 31)) & 1u) {
-							const uint32_t mult = verify_window(a, key, tile_start + lane * kLane + p);
+				for (int g = 0; g < Front::kWords; g++)
+					for (uint32_t w = fr.hw[g]; w; w &= w - 1)
+						lst[k++] = (uint16_t) (lane * kLane + Front::sym_of(g, __ffs(w) - 1));
+				__syncwarp();
+				for (uint32_t base = 0; base < tot_c; base += 32) {
+					const uint32_t i = base + lane;
+					uint32_t cpos = 0, sv = 0, mu = 0;
+					if (i < tot_c) {
+						cpos = lst[i];
+						uint32_t rm = fr.probe_mask(a, buf, pk, cpos);
+						while (rm) {
+							const uint32_t r = (uint32_t) (__ffs(rm) - 1);
+							rm &= rm - 1;
+							const uint32_t mult = check_end(cpos + r);
 							if (mult) {
-								const uint32_t bit = 1u << (p & 31);
-								if (p < 32)
-									mw0 |= bit;
-								else if (p < 64)
-									mw1 |= bit;
-								else if (p < 96)
-									mw2 |= bit;
-								else
-									mw3 |= bit;
+								sv |= 1u << r;
+								mu |= mult > 1;
+							}
+						}
+					}
+					// survivors (rare) go back to the lane whose chunk they end in
+					uint32_t any = __ballot_sync(kFull, sv != 0);
+					while (any) {
+						const int src = __ffs(any) - 1;
+						any &= any - 1;
+						const uint32_t cp = __shfl_sync(kFull, cpos, src);
+						uint32_t sb = __shfl_sync(kFull, sv, src);
+						const uint32_t m2 = __shfl_sync(kFull, mu, src);
+						const uint32_t owner = cp / kLane;
+						if (lane == owner) {
+							const uint32_t c = cp - owner * kLane;
+							for (; sb; sb &= sb - 1)
+								set_mw(c + (uint32_t) (__ffs(sb) - 1));
+							multi |= m2;
+						}
+					}
+				}
+				__syncwarp(); // the list is reused for the match positions below
+			} else {
+				// many candidates: every lane checks its own
+#pragma unroll
+				for (int g = 0; g < Front::kWords; g++) {
+					uint32_t w = fr.hw[g];
+					while (w) {
+						const int b = __ffs(w) - 1;
+						w &= w - 1;
+						const uint32_t c = Front::sym_of(g, b);
+						uint32_t rm = fr.probe_mask(a, buf, pk, lane * kLane + c);
+						while (rm) {
+							const uint32_t p = c + (uint32_t) (__ffs(rm) - 1);
+							rm &= rm - 1;
+							const uint32_t mult = check_end(lane * kLane + p);
+							if (mult) {
+								set_mw(p);
 								multi |= mult > 1;
 							}
 						}
@@ -318,6 +389,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		if constexpr (!kPacked)
 			refill(slot);
 	}
+	if (a.trace && lane == 0) {
+		trace_mark(a, 48 + warp);
+		a.trace[(size_t) blockIdx.x * kTraceWords + 80 + warp] = n_scanned;
+	}
+	if (!tab_ready)
+		mbar_wait(tab_bar, 0); // a warp without a tile: the CTA must not retire under its own table copy
 	if (a.pdl && !waited)
 		pdl_wait(); // the previous scan is complete: the scratch arrays and the control block are ours now
 	em.finish();
@@ -331,6 +408,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			atomicOr(s_bad, 1u);
 	}
 	__syncthreads();
+	if (threadIdx.x == 0)
+		trace_mark(a, 4);
 
 	// ---- order, part 1: exclusive prefix of the per-tile counts inside this CTA's span
 	const uint32_t G = gridDim.x;
@@ -363,8 +442,13 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		__syncthreads();
 	}
 
-	// ---- arrive: count + grid barrier + exit ticket in one atomic; the last CTA publishes
+	// ---- arrive: count + grid barrier + exit ticket + ordering slot in one atomic; the last CTA publishes.
+	// Who orders the staged matches: every CTA that arrives after the staging cursor has passed kSoloStage
+	// (the cursor only grows, and the CTA that reads it last reads its final value, so either somebody stays
+	// or at most kSoloStage slots are staged and the last CTA to arrive places them alone).  Everybody else
+	// retires at once: no grid-wide wait for a scan with few matches, its SMs go to the next scan of the stream.
 	bool publisher = false;
+	uint32_t *s_order = reinterpret_cast<uint32_t *>(smem + 48); // [0] orders?, [1] slot, [2] CTAs ordering
 	// the previous scan's counts have had a whole scan to arrive (the last one is collected by acwm_fetch_global_count)
 	auto collect_peers = [&]() {
 		if (a.xepoch < 2)
@@ -391,12 +475,20 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		s_misc[1] = old_written;
 		if (*s_bad)
 			atomicOr(&wk->bad_text, 1u);
+		trace_mark(a, 5);
+		unsigned long long stay = 0;
+		if (a.want_positions)
+			stay = (!(a.tune & kTuneEarlyRetire) || __ldcg(&wk->cursor) > kSoloStage) ? 1ull : 0ull;
 		__threadfence();
 		const unsigned long long mine = *s_count;
-		const unsigned long long before = atomicAdd(&wk->arrive, (1ull << kArriveShift) + mine);
-		if ((before >> kArriveShift) == G - 1) { // everybody has arrived: totals are final
+		const unsigned long long before = atomicAdd(&wk->arrive, (1ull << kArriveShift) + (stay << kStayShift) + mine);
+		trace_mark(a, 6);
+		const bool last = (before >> kArriveShift) == G - 1;
+		uint32_t order_slot = (uint32_t) (before >> kStayShift) & 0x1ffu; // CTAs that stay and arrived before us
+		uint32_t order_n = 0, orders = 0;
+		if (last) { // everybody has arrived: totals are final
 			__threadfence();
-			const unsigned long long cnt = (before & ((1ull << kArriveShift) - 1)) + mine;
+			const unsigned long long cnt = (before & kArriveCountMask) + mine;
 			const unsigned long long cur = __ldcg(&wk->cursor);
 			unsigned long long r_written = old_written;
 			unsigned int r_ovf = old_ovf;
@@ -412,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			res->bad_text = old_bad | __ldcg(&wk->bad_text);
 			res->overflow = r_ovf;
 			if (a.world > 1) { // hand this launch's count to every rank (ours included)
-				const unsigned long long tagged = ((unsigned long long) (a.xepoch & 0xffffu) << kArriveShift) | cnt;
+				const unsigned long long tagged = ((unsigned long long) (a.xepoch & 0xffffu) << kMailShift) | cnt;
 				const uint32_t slot = (a.xepoch & (kPeerRing - 1)) * a.world + a.rank;
 				for (uint32_t r = 0; r < a.world; r++)
 					st_relaxed_sys_u64(a.peers[r] + slot, tagged);
@@ -421,17 +513,32 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 				res->global_count = old_count + cnt;
 		}
 		if (a.want_positions) {
-			while ((ld_acquire_u64(&wk->arrive) >> kArriveShift) < G)
-				__nanosleep(32);
-			__threadfence();
+			if (stay) {
+				unsigned long long v;
+				while (((v = ld_acquire_u64(&wk->arrive)) >> kArriveShift) < G)
+					__nanosleep(32);
+				__threadfence();
+				order_n = (uint32_t) (v >> kStayShift) & 0x1ffu;
+				orders = 1;
+			} else if (last && order_slot == 0) { // nobody stayed: at most kSoloStage slots, placed by this CTA alone
+				order_n = 1;
+				orders = 1;
+			}
 		}
+		s_order[0] = orders;
+		s_order[1] = order_slot;
+		s_order[2] = order_n;
+		trace_mark(a, 7);
 	}
-	if (!a.want_positions) {
+	if (a.want_positions)
+		__syncthreads();
+	if (!a.want_positions || !s_order[0]) {
+		if (threadIdx.x == 0)
+			trace_mark(a, 8);
 		if (publisher)
 			collect_peers();
 		return;
 	}
-	__syncthreads();
 
 	// ---- order, part 2: span bases = exclusive prefix of the per-CTA totals, then the scatter
 	unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_warps); // the ring buffers are free now
@@ -464,19 +571,34 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	__syncthreads();
 	const unsigned long long cursor = s_misc[0];
 	const uint64_t staged = cursor < a.stage_cap ? cursor : a.stage_cap;
-	const uint64_t stride = (uint64_t) G * THREADS;
-	for (uint64_t i = (uint64_t) blockIdx.x * THREADS + threadIdx.x; i < staged; i += stride) {
-		const uint64_t e = __ldcg(a.staging + i);
-		if (e == ~0ull)
-			continue; // unused tail of a warp's reservation
-		const uint64_t tile = e >> (kRankBits + kPosBits);
-		const uint32_t rank = (uint32_t) (e >> kPosBits) & ((1u << kRankBits) - 1);
-		const uint32_t pos = (uint32_t) e & ((1u << kPosBits) - 1);
-		const uint64_t owner = (tile - a.tile_lo) / a.tiles_per_cta;
-		const uint64_t at = s_base[owner] + __ldcg(a.tile_count + tile) + rank;
-		if (at < a.cap)
-			a.positions[at] = tile * kTile + pos - a.data_lo;
+	const uint64_t stride = (uint64_t) s_order[2] * THREADS;
+	constexpr int kBatch = 4; // staged entries in flight per thread (the lone CTA of a sparse scan places up to kSoloStage of them)
+	for (uint64_t i0 = (uint64_t) s_order[1] * THREADS + threadIdx.x; i0 < staged; i0 += kBatch * stride) {
+		uint64_t e[kBatch];
+		uint32_t tc[kBatch];
+#pragma unroll
+		for (int u = 0; u < kBatch; u++) {
+			const uint64_t i = i0 + (uint64_t) u * stride;
+			e[u] = i < staged ? __ldcg(a.staging + i) : ~0ull; // all-ones: unused tail of a warp's reservation
+		}
+#pragma unroll
+		for (int u = 0; u < kBatch; u++)
+			tc[u] = e[u] != ~0ull ? __ldcg(a.tile_count + (e[u] >> (kRankBits + kPosBits))) : 0u;
+#pragma unroll
+		for (int u = 0; u < kBatch; u++) {
+			if (e[u] == ~0ull)
+				continue;
+			const uint64_t tile = e[u] >> (kRankBits + kPosBits);
+			const uint32_t rank = (uint32_t) (e[u] >> kPosBits) & ((1u << kRankBits) - 1);
+			const uint32_t pos = (uint32_t) e[u] & ((1u << kPosBits) - 1);
+			const uint64_t owner = (tile - a.tile_lo) / a.tiles_per_cta;
+			const uint64_t at = s_base[owner] + tc[u] + rank;
+			if (at < a.cap)
+				a.positions[at] = tile * kTile + pos - a.data_lo;
+		}
 	}
+	if (threadIdx.x == 0)
+		trace_mark(a, 8);
 	if (publisher)
 		collect_peers();
 }

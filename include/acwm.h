@@ -166,6 +166,13 @@ int acwm_fetch_global_count(acwm_matcher *mt, uint64_t *global_count, void *stre
 int acwm_set_profiling(acwm_matcher *mt, int on);
 int acwm_profiled_seconds(acwm_matcher *mt, double *scan_s, double *finalize_s);
 
+/* Kernel timeline instrumentation: d_trace = device buffer of acwm_trace_words_per_cta() uint64 per CTA
+ * of the scan grid (<= 256 CTAs), or NULL = off.  Every CTA of the following scans stores %globaltimer
+ * stamps of its phases there (entry, prologue, tables ready, scan done, arrival, exit; per warp: first tile
+ * ready, scan loop done, tiles scanned); scripts/trace.py reads them back. */
+int acwm_set_trace(acwm_matcher *mt, unsigned long long *d_trace);
+uint32_t acwm_trace_words_per_cta(void);
+
 /* Kernels this matcher has launched so far (scan + finalize), for bench reports. */
 unsigned long long acwm_launch_count(const acwm_matcher *mt);
 
@@ -195,6 +202,31 @@ enum {
 	ACWM_BLOB_RMASK = 7       /* WM, stride > 1: offset masks of the candidate blocks (uint8, uint16 for stride 16) */
 };
 int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_t *bytes);
+
+/* ------------- data files (host only): the driver's side of the path, main.c:31-123,453 -------------
+ * The reference's tables are indexed by the text bytes themselves (ac/ac.c:136,209; wu/wu.c:63-67), so
+ * a corpus reaches the scan as symbol codes in [0, alphabet).  These replace the helpers the reference
+ * calls but does not ship (load_files, create_multiple_pattern_with_hits: main.c:49,453). */
+
+/* Raw byte -> symbol code for the corpora of main.c:38-110; 0xff = not a symbol (dropped by the loader).
+ * 2 / 8: digits '0'..; 4: ACGT (either case, U = T); 20: the amino-acid letters ACDEFGHIKLMNPQRSTVWY;
+ * 128: 7-bit ASCII; 256: identity. */
+int acwm_symbol_map(uint32_t alphabet, uint8_t map[256]);
+/* Encode n_raw corpus bytes into symbol codes (out may alias raw; at most n_raw codes).  Bytes that are
+ * already all < alphabet pass through unchanged; FASTA '>' lines and non-symbols are dropped. */
+int acwm_encode_symbols(const uint8_t *raw, uint64_t n_raw, uint32_t alphabet, uint8_t *out, uint64_t *n_out);
+/* Load a corpus file as symbol codes (malloc'ed; release with acwm_free_text); max_symbols = 0: all of it,
+ * else the first max_symbols (the reference's -n). */
+int acwm_load_text(const char *path, uint32_t alphabet, uint64_t max_symbols, uint8_t **text, uint64_t *n);
+void acwm_free_text(uint8_t *text);
+/* p patterns of m symbols into patterns[p*m] (the flat pattern2 layout, main.c:455-461): hit_percent of
+ * them are windows of the text at seeded offsets (they occur), the rest uniform symbols. */
+int acwm_patterns_with_hits(const uint8_t *text, uint64_t n, uint32_t m, uint32_t p, uint32_t alphabet, uint64_t seed,
+		uint32_t hit_percent, uint8_t *patterns);
+/* select_data_file (main.c:31-123): the text size n selects the corpus under data_root (NULL =
+ * "../data-cuda-multi"), the alphabet must fit it; pattern file = pattern/<n>/<m>/<alphabet>/pattern. */
+int acwm_select_data_file(uint32_t m, uint64_t n, uint32_t alphabet, const char *data_root, char *pattern_path,
+		char *text_path, size_t path_cap);
 
 /* One pattern in the verification buckets. */
 typedef struct acwm_ventry {
