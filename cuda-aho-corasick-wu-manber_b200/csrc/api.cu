@@ -55,8 +55,9 @@ static int ensure_positions(acwm_matcher *mt, uint64_t cap) {
 	mt->d_staging = mt->d_positions = nullptr;
 	mt->pos_cap = 0;
 	// staging: one reservation block of slack per warp the widest grid can hold
-	mt->stage_cap = cap + (uint64_t) kStageBlock * 32 * (uint64_t) std::max(mt->sm_count, 1);
-	CU(cudaMalloc((void **) &mt->d_staging, mt->stage_cap * 8));
+	// a warp's reservations double in size: at most as many slots idle as it fills, plus its first block
+	mt->stage_cap = 2 * cap + (uint64_t) 2 * kStageBlock * 32 * (uint64_t) std::max(mt->sm_count, 1);
+	CU(cudaMalloc((void **) &mt->d_staging, 2 * mt->stage_cap * 8)); // two copies, by launch parity (see Work)
 	CU(cudaMalloc((void **) &mt->d_positions, cap * 8));
 	mt->pos_cap = cap;
 	return ACWM_OK;
@@ -70,7 +71,7 @@ static int ensure_tiles(acwm_matcher *mt, uint64_t n_tiles) {
 	mt->d_tile_count = nullptr;
 	mt->tile_cap = 0;
 	const uint64_t want = n_tiles + n_tiles / 8 + 1024;
-	CU(cudaMalloc((void **) &mt->d_tile_count, want * 4));
+	CU(cudaMalloc((void **) &mt->d_tile_count, 2 * want * 4)); // two copies, by launch parity
 	mt->tile_cap = want;
 	return ACWM_OK;
 }
@@ -116,7 +117,7 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	CU(cudaMalloc((void **) &mt->d_ctl, sizeof(Control)));
 	CU(cudaMemset(mt->d_ctl, 0, sizeof(Control)));
 	CU(cudaMallocHost((void **) &mt->h_res, sizeof(Result)));
-	CU(cudaMalloc((void **) &mt->d_cta_total, kMaxScanBlocks * sizeof(unsigned long long)));
+	CU(cudaMalloc((void **) &mt->d_cta_total, 2 * kMaxScanBlocks * sizeof(unsigned long long)));
 	CU(cudaStreamCreateWithFlags(&mt->s_copy, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&mt->s_scan, cudaStreamNonBlocking));
 	for (auto &e : mt->ev_copy)
@@ -150,11 +151,11 @@ static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
 }
 
 // Kernel variants that can be switched off for A/B measurements (scripts/tune.py): ACWM_TUNE = OR of
-// 1 (warp-cooperative candidate verification) and 2 (CTAs of a sparse scan retire without the grid wait).
+// 1 (warp-cooperative candidate verification).
 static uint32_t kernel_tune() {
 	static const uint32_t v = [] {
 		const char *e = getenv("ACWM_TUNE");
-		return e && *e ? (uint32_t) strtoul(e, nullptr, 0) : (kTuneCoopVerify | kTuneEarlyRetire);
+		return e && *e ? (uint32_t) strtoul(e, nullptr, 0) : kTuneCoopVerify;
 	}();
 	return v;
 }
@@ -183,17 +184,17 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.patterns = mt->d_patterns;
 	a.prm = c.prm;
 	a.ctl = mt->d_ctl;
-	a.staging = mt->d_staging;
+	const uint32_t par = mt->epoch & 1u; // the scratch arrays of this launch (its predecessor may still be reading the others)
+	a.staging = mt->d_staging ? mt->d_staging + par * mt->stage_cap : nullptr;
 	a.positions = mt->d_positions;
 	a.cap = want_positions ? mt->pos_cap : 0;
 	a.stage_cap = want_positions ? mt->stage_cap : 0;
-	a.tile_count = mt->d_tile_count;
-	a.cta_total = mt->d_cta_total;
+	a.tile_count = mt->d_tile_count ? mt->d_tile_count + par * mt->tile_cap : nullptr;
+	a.cta_total = mt->d_cta_total + par * kMaxScanBlocks;
 	a.stages = c.info.stages;
 	a.epoch = mt->epoch++;
 	a.want_positions = want_positions;
 	a.append = append;
-	a.pdl = (exchange && mt->overlap) ? 1 : 0; // device-resident scans only (exchange == "called from acwm_scan_device")
 	a.tune = kernel_tune();
 	a.trace = mt->d_trace;
 	if (exchange && mt->peer_world > 1) {
@@ -213,6 +214,10 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	// per-tile counts of a span stay in whatever shared memory the tables and the rings leave free
 	a.cnt_cap = (uint32_t) std::min<uint64_t>(a.tiles_per_cta, (kMaxSmem - c.info.smem_bytes) / 4);
 	const uint32_t smem = c.info.smem_bytes + a.cnt_cap * 4;
+	// overlap mode (device-resident scans only; exchange == "called from acwm_scan_device"): a programmatic
+	// dependent launch, for grids that fill the GPU with CTAs that own their SM -- what keeps at most two
+	// consecutive scans in flight (see Work in scan_common.cuh)
+	a.pdl = (exchange && mt->overlap && grid == (uint32_t) mt->sm_count && 2 * (smem + 1024) > kMaxSmem + 1024) ? 1 : 0;
 	cudaError_t e = c.prm.packed2bit ? launch_scan_packed(a, threads, smem, grid, st)
 									 : launch_scan_bytes(a, threads, smem, grid, st);
 	if (e != cudaSuccess)
@@ -293,6 +298,7 @@ int acwm_scan_device(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64
 				CU(cudaEventCreate(&e));
 		CU(cudaEventRecord(mt->ev_prof[0], st));
 	}
+	mt->first_epoch = mt->epoch;
 	if ((rc = launch_scan(mt, d_text, n, report_from, 0, n_tiles, want_positions, 0, 1, st)))
 		return rc;
 	if (mt->profiling)
@@ -313,6 +319,8 @@ int acwm_fetch(acwm_matcher *mt, uint64_t *count, uint64_t *positions, uint64_t 
 		*count = h.count;
 	if (n_written)
 		*n_written = 0;
+	if (h.order_failed > mt->first_epoch)
+		return set_error(ACWM_ERR_CUDA, "the position ordering gave up waiting for a CTA of its own launch");
 	if (h.bad_text)
 		return set_error(ACWM_ERR_BAD_TEXT, "text holds a byte >= 4 but the matcher was built for alphabet <= 4");
 	if (positions && mt->last_want_positions) {
@@ -372,6 +380,7 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		mt->ev_time.push_back(e);
 	}
 	apply_l2_window(mt, mt->s_scan);
+	mt->first_epoch = mt->epoch;
 	for (uint64_t ci = 0; ci < n_chunks; ci++) {
 		const uint64_t b0 = std::min<uint64_t>(n, ci * chunk_tiles * T), b1 = std::min<uint64_t>(n, (ci + 1) * chunk_tiles * T);
 		if (b1 > b0)

@@ -21,19 +21,21 @@ constexpr uint32_t kMaxStages = 4;
 constexpr uint32_t kMaxPeers = 16;                  // ranks of the in-kernel count exchange
 constexpr uint32_t kPeerRing = 4;                   // mailbox slots per rank pair: epochs in flight
 constexpr uint32_t kListCap = 64;                   // per-warp list of match positions of one tile (cooperative stores)
+constexpr uint32_t kLogCap = 24;                    // per-warp log of its staging reservations (they double in size)
+constexpr uint32_t kMaxGrabLog2 = 23;               // largest single reservation: 2^23 slots
 
 // per-warp shared memory: ring of raw tiles, (2-bit path) 2-bit copy of the current tile for the
-// verification windows, one mbarrier + one tile id per ring slot, match list
+// verification windows, one mbarrier + one tile id per ring slot, match list, reservation log
 constexpr uint32_t warp_smem_bytes(uint32_t stages, bool packed) {
-	return stages * kBufBytes + (packed ? kPackWords * 4 : 0) + kMaxStages * 16 + kListCap * 2;
+	return stages * kBufBytes + (packed ? kPackWords * 4 : 0) + kMaxStages * 16 + kListCap * 2 + kLogCap * 8;
 }
 
 constexpr uint32_t kMaxSmem = 227 * 1024;
 constexpr uint32_t kSmemReserve = 1024;             // CTA-level scratch (barriers, finalize scan), alignment slack
 
-// Staging entry: [tile:28 | rank:22 | pos_in_tile:14]; all-ones = unused slot
+// Staging entry: [tile:28 | rank:22 | pos_in_tile:14]
 constexpr uint32_t kPosBits = 14, kRankBits = 22;
-constexpr uint32_t kStageBlock = 32;                // staging slots a warp reserves per atomic
+constexpr uint32_t kStageBlock = 32;                // staging slots of a warp's first reservation (each further one doubles)
 
 // (warps, stages) the scan kernel is launched with, in order of preference.  The 2-bit path
 // copies a tile into registers first and refills its slot while it walks, so one slot per

@@ -54,6 +54,7 @@ struct acwm_matcher {
 	bool overlap = false;
 	unsigned long long *d_trace = nullptr; // acwm_set_trace (caller-owned device buffer)
 	uint32_t epoch = 0;
+	uint32_t first_epoch = 0; // launch number of the first launch of the last search (acwm_fetch: did its ordering fail?)
 	// multi-GPU count exchange (acwm_set_peers)
 	uint32_t peer_world = 0, peer_rank = 0, xepoch = 0;
 	uint64_t peer_ptrs[acwm::kMaxPeers] = {};

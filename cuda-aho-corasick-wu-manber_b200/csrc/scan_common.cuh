@@ -16,32 +16,37 @@ struct Result {
 	unsigned int overflow;       // more matches than position capacity
 	unsigned long long global_count; // sum of `count` over the ranks of the peer exchange (== count without peers)
 	unsigned int global_epoch;   // exchange epoch global_count belongs to
-	unsigned int pad;
+	unsigned int order_failed;   // launch number + 1 of the last scan whose position ordering gave up (never in practice)
 };
 
-// Working counters of the launch in flight.  Two copies: launch k uses work[k & 1] and
-// clears work[(k + 1) & 1] for its successor (which starts only after k is done), so no
-// memset node is needed between scans.
+// Working counters of the launch in flight.  Three copies: launch k uses work[k % 3] and clears
+// work[(k + 1) % 3] when it STARTS (before it lets its successor in).  In overlap mode two
+// consecutive launches run at the same time (never three: a full grid of one-per-SM CTAs only finds room
+// as its predecessor's CTAs exit, and those exit only after THEIR predecessor has completed), so the copy
+// being cleared belongs to a launch that is over and the successor finds its copy zeroed.  No memset node
+// between scans.  The scratch arrays the scan phase writes (staging, per-tile counts, per-CTA totals)
+// exist twice, selected by launch parity, for the same reason.
 struct Work {
-	unsigned long long arrive;   // [CTAs arrived : 9 | of which order the positions : 9 | matches : 46] -- one atomic per CTA is
-	                             // count, grid barrier, exit ticket and the CTA's slot in the ordering epilogue
+	unsigned long long arrive;   // [CTAs arrived : 16 | matches : 48] -- one atomic per CTA is count, grid barrier, exit
+	                             // ticket and (by arrival order) the CTA's role in the ordering epilogue
 	unsigned long long cursor;   // staging slots handed out
 	unsigned int bad_text;
 	unsigned int pad[3];
 };
-constexpr unsigned kArriveShift = 55, kStayShift = 46; // grids of up to 256 CTAs
-constexpr unsigned long long kArriveCountMask = (1ull << kStayShift) - 1;
+constexpr unsigned kArriveShift = 48;
+constexpr unsigned long long kArriveCountMask = (1ull << kArriveShift) - 1;
 constexpr unsigned kMailShift = 48;   // mailbox word of the count exchange: [epoch tag : 16 | count : 48]
-// A CTA that arrives while at most this many staging slots are handed out does not wait for the grid: it retires
-// (the next scan of the stream takes over its SM) and leaves the ordering to the CTAs that arrive after the
-// staging cursor has passed the mark -- or, when none has, to the last CTA to arrive, alone.
-constexpr unsigned long long kSoloStage = 4096;
+// Per-CTA totals carry the launch number, so a stale value is never mistaken for this launch's: [tag : 24 | matches : 40]
+constexpr unsigned kTotalShift = 40;
+constexpr unsigned long long kTotalMask = (1ull << kTotalShift) - 1;
+constexpr unsigned long long kLookbackTimeoutNs = 200ull * 1000 * 1000; // a predecessor that never shows up: report, do not hang
+// Work.bad_text bits: 1 = text byte >= 4 on the 2-bit path, 4 = a warp's reservation log overflowed (reported as overflow)
 // ScanArgs.tune bits
-constexpr uint32_t kTuneCoopVerify = 1u, kTuneEarlyRetire = 2u;
+constexpr uint32_t kTuneCoopVerify = 1u;
 
 struct Control {
 	Result result;
-	Work work[2];
+	Work work[3];
 };
 
 struct ScanArgs {
@@ -190,18 +195,20 @@ __device__ __forceinline__ void trace_mark(const ScanArgs &a, uint32_t slot) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Warp-level staging of the matches of one tile.  A warp reserves staging slots in blocks
-// (one atomic per >= kStageBlock matches instead of one per tile) and leaves the unused
-// tail of its last block marked with all-ones.
+// Warp-level staging of the matches of one tile.  A warp reserves staging slots from the launch's cursor in
+// blocks that double in size (one global atomic per block, not per tile) and logs its blocks in shared
+// memory: when the scan is over the warp itself moves its matches to their sorted places.
 struct Emitter {
 	const ScanArgs *a;
 	Work *wk;
 	uint32_t *s_cnt;             // shared-memory per-tile counts (first a->cnt_cap tiles of the span)
+	unsigned long long *log;     // this warp's reservations: [slots : 24 | first slot : 40]
 	uint64_t tile;
 	uint32_t idx;                // span-relative index of the tile
 	unsigned long long warp_count;
 	unsigned long long blk_ptr, old_ptr, new_ptr;
 	uint32_t blk_left, old_left;
+	uint32_t n_log, lost;        // reservations logged / more reservations than the log holds (reported as overflow)
 
 	// warp-uniform: make room for `total` entries of the current tile
 	__device__ __forceinline__ void reserve(uint32_t total) {
@@ -210,10 +217,17 @@ struct Emitter {
 		new_ptr = 0;
 		if (total > blk_left) {
 			const uint32_t extra = total - blk_left;
-			const uint32_t grab = max(extra, kStageBlock);
+			const uint32_t grab = max(extra, kStageBlock << min(n_log, kMaxGrabLog2 - 5u));
 			unsigned long long p = 0;
-			if (lane_id() == 0)
+			if (lane_id() == 0) {
 				p = atomicAdd(&wk->cursor, (unsigned long long) grab);
+				if (n_log < kLogCap)
+					log[n_log] = ((unsigned long long) grab << 40) | p;
+			}
+			if (n_log < kLogCap)
+				n_log++;
+			else
+				lost = 1;
 			new_ptr = __shfl_sync(kFull, p, 0);
 			blk_ptr = new_ptr + extra;
 			blk_left = grab - extra;
@@ -237,9 +251,10 @@ struct Emitter {
 		}
 		warp_count += total;
 	}
+	// blocks fill up in order: only the last one has an unused tail
 	__device__ __forceinline__ void finish() const {
-		if (a->want_positions && lane_id() < blk_left && blk_ptr + lane_id() < a->stage_cap)
-			a->staging[blk_ptr + lane_id()] = ~0ull;
+		if (lane_id() == 0 && n_log && !lost)
+			log[n_log - 1] -= (unsigned long long) blk_left << 40;
 	}
 };
 

@@ -33,10 +33,13 @@ static __device__ __noinline__ void load_tile_edge(const ScanArgs &a, uint64_t t
 	const long long base = (long long) (tile * (uint64_t) kTile) - (long long) kHalo;
 	for (int c = (int) lane_id(); c < (int) (kLoadBytes / 16); c += 32) {
 		const long long off = base + 16ll * c;
+		if (off >= (long long) a.data_lo && off + 16 <= (long long) a.data_hi) {
+			// whole 16-byte pieces: asynchronous copies, all in flight together, no registers held
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(buf + 16 * c)), "l"(a.text16 + off) : "memory");
+			continue;
+		}
 		uint4 r = make_uint4(0, 0, 0, 0);
-		if (off >= (long long) a.data_lo && off + 16 <= (long long) a.data_hi)
-			r = ldg_stream16(a.text16 + off);
-		else if (off + 16 > (long long) a.data_lo && off < (long long) a.data_hi) {
+		if (off + 16 > (long long) a.data_lo && off < (long long) a.data_hi) { // straddles an end of the text
 			uint32_t w[4] = {0, 0, 0, 0};
 			for (int k = 0; k < 16; k++) {
 				const long long pos = off + k;
@@ -47,6 +50,7 @@ static __device__ __noinline__ void load_tile_edge(const ScanArgs &a, uint64_t t
 		}
 		*reinterpret_cast<uint4 *>(buf + 16 * c) = r;
 	}
+	asm volatile("cp.async.wait_all;" ::: "memory"); // the caller's __syncwarp publishes the tile to the warp
 }
 
 __device__ __forceinline__ bool tile_is_interior(const ScanArgs &a, uint64_t tile) {
@@ -82,12 +86,22 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + stages * kBufBytes + (kPacked ? kPackWords * 4 : 0));
 	uint32_t *s_tid = reinterpret_cast<uint32_t *>(bars + kMaxStages); // span-relative tile index per ring slot
 	uint16_t *lst = reinterpret_cast<uint16_t *>(bars + 2 * kMaxStages);  // match positions of the current tile
+	unsigned long long *wlog = reinterpret_cast<unsigned long long *>(lst + kListCap); // this warp's staging reservations
 	uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_warps + W * warp_smem_bytes(stages, kPacked)); // a.cnt_cap words
 
+	// this CTA's span of warp tiles; the warps claim its tiles one at a time (shared-memory ticket)
+	const uint64_t cta_lo = min(a.tile_lo + (uint64_t) blockIdx.x * a.tiles_per_cta, a.tile_hi);
+	const uint64_t cta_hi = min(cta_lo + a.tiles_per_cta, a.tile_hi);
+	const uint32_t n_b = (uint32_t) (cta_hi - cta_lo);
+	const uint64_t stream_pol = policy_evict_first();
+	const uint32_t tab_bytes = front_smem + rm_bytes + f2_bytes;
+
+	// ---- prologue: every warp arms its own barriers and starts its first tile(s) at once (static claims
+	// warp, W + warp, ..); the CTA meets only afterwards, under the copies
 	if (threadIdx.x == 0) {
 		trace_mark(a, 0);
 		mbar_init(tab_bar, 1);
-		*s_next = 0;
+		*s_next = stages * W;
 		*s_bad = 0;
 		*s_count = 0;
 	}
@@ -100,41 +114,13 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	if (kPacked && lane < 3)
 		pk[kPackWords - 3 + lane] = 0;
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	__syncthreads();
-	if (threadIdx.x == 0)
-		trace_mark(a, 1);
-	if (a.pdl)
-		pdl_trigger(); // overlap mode: the next scan of the stream may take over SMs as our CTAs retire
-
-	// tables: global -> shared with TMA bulk copies, overlapped with the first text tiles
-	const uint32_t tab_bytes = front_smem + rm_bytes + f2_bytes;
-	if (threadIdx.x == 0 && tab_bytes) {
-		const uint64_t keep = policy_evict_last();
-		mbar_expect_tx(tab_bar, tab_bytes);
-		for (uint32_t off = 0; off < front_smem; off += 16384)
-			tma_bulk_g2s(s_front + off, a.front + off, min(16384u, front_smem - off), tab_bar, keep);
-		for (uint32_t off = 0; off < rm_bytes; off += 16384)
-			tma_bulk_g2s(s_rmask + off, a.rmask + off, min(16384u, rm_bytes - off), tab_bar, keep);
-		for (uint32_t off = 0; off < f2_bytes; off += 16384)
-			tma_bulk_g2s(reinterpret_cast<uint8_t *>(s_f2) + off, reinterpret_cast<const uint8_t *>(a.filter2) + off,
-					min(16384u, f2_bytes - off), tab_bar, keep);
-	}
-
-	// this CTA's span of warp tiles; the warps claim its tiles one at a time (shared-memory ticket)
-	const uint64_t cta_lo = min(a.tile_lo + (uint64_t) blockIdx.x * a.tiles_per_cta, a.tile_hi);
-	const uint64_t cta_hi = min(cta_lo + a.tiles_per_cta, a.tile_hi);
-	const uint32_t n_b = (uint32_t) (cta_hi - cta_lo);
-	const uint64_t stream_pol = policy_evict_first();
+	__syncwarp();
 
 	uint32_t tma_mask = 0, phase_mask = 0;
-	// claim the next tile of the span for ring slot s and start loading it
-	auto refill = [&](uint32_t s) {
-		uint32_t idx = 0;
-		if (lane == 0) {
-			idx = atomicAdd(s_next, 1u);
+	// start loading tile idx of the span (if there is one) into ring slot s
+	auto issue = [&](uint32_t s, uint32_t idx) {
+		if (lane == 0)
 			s_tid[s] = idx;
-		}
-		idx = __shfl_sync(kFull, idx, 0);
 		if (idx >= n_b)
 			return;
 		const uint64_t t = cta_lo + idx;
@@ -153,16 +139,52 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			tma_mask &= ~(1u << s);
 		}
 	};
-
+	// claim the next tile of the span for ring slot s and start loading it
+	auto refill = [&](uint32_t s) {
+		uint32_t idx = 0;
+		if (lane == 0)
+			idx = atomicAdd(s_next, 1u);
+		issue(s, __shfl_sync(kFull, idx, 0));
+	};
 	for (uint32_t s = 0; s < stages; s++)
-		refill(s);
-	__syncwarp();
-	if (threadIdx.x == 0)
+		issue(s, s * W + warp);
+
+	// tables: global -> shared with TMA bulk copies, overlapped with the first text tiles
+	if (threadIdx.x == 0) {
+		if (tab_bytes) {
+			const uint64_t keep = policy_evict_last();
+			mbar_expect_tx(tab_bar, tab_bytes);
+			for (uint32_t off = 0; off < front_smem; off += 16384)
+				tma_bulk_g2s(s_front + off, a.front + off, min(16384u, front_smem - off), tab_bar, keep);
+			for (uint32_t off = 0; off < rm_bytes; off += 16384)
+				tma_bulk_g2s(s_rmask + off, a.rmask + off, min(16384u, rm_bytes - off), tab_bar, keep);
+			for (uint32_t off = 0; off < f2_bytes; off += 16384)
+				tma_bulk_g2s(reinterpret_cast<uint8_t *>(s_f2) + off, reinterpret_cast<const uint8_t *>(a.filter2) + off,
+						min(16384u, f2_bytes - off), tab_bar, keep);
+		}
+		trace_mark(a, 1);
+	}
+	if (blockIdx.x == 0 && threadIdx.x == THREADS - 1) {
+		// the successor's counters (see Work): zero in L2 before the successor may start (it may once every CTA
+		// of ours has passed the trigger below); done by a lane that has nothing to issue, under the first copies
+		Work *nxt = &a.ctl->work[(a.epoch + 1u) % 3u];
+		__stcg(&nxt->arrive, 0ull);
+		__stcg(&nxt->cursor, 0ull);
+		__stcg(&nxt->bad_text, 0u);
+		__threadfence();
+	}
+	__syncthreads(); // the ticket, the table barrier and the CTA counters are set up
+	if (a.pdl)
+		pdl_trigger(); // overlap mode: the next scan of the stream may take over SMs as our CTAs retire
+	if (threadIdx.x == 0) {
 		trace_mark(a, 2);
+		trace_mark(a, 9);
+		trace_mark(a, 10); // 2 -> 9 -> 10: what a stamp itself costs
+	}
 	uint32_t n_scanned = 0;
 
 	uint32_t badacc = 0;
-	Work *wk = &a.ctl->work[a.epoch & 1u];
+	Work *wk = &a.ctl->work[a.epoch % 3u];
 	Emitter em;
 	em.a = &a;
 	em.wk = wk;
@@ -172,11 +194,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	em.warp_count = 0;
 	em.blk_ptr = em.old_ptr = em.new_ptr = 0;
 	em.blk_left = em.old_left = 0;
+	em.log = wlog;
+	em.n_log = em.lost = 0;
 	Front fr;
 	const uint32_t *f2 = a.prm.f2_in_smem ? s_f2 : a.filter2;
 	fr.init(s_front, a.prm.r_in_smem ? s_rmask : a.rmask, a);
 
-	bool waited = false;
 	bool tab_ready = tab_bytes == 0; // the tables are first needed by walk(): the first tile is loaded and packed under their copy
 	for (uint32_t slot = 0;; slot = slot + 1 == stages ? 0 : slot + 1) {
 		const uint32_t idx = s_tid[slot];
@@ -208,12 +231,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 
 		em.tile = tile;
 		em.idx = idx;
-		// overlap mode: up to here the warp has only read (text, tables); the previous scan of the stream may
-		// still be ordering its matches in the scratch arrays we are about to write
-		if (a.pdl && !waited && (idx >= a.cnt_cap || __any_sync(kFull, fr.count() != 0))) {
-			pdl_wait();
-			waited = true;
-		}
+		// overlap mode: the previous scan of the stream may still be ordering its matches -- in ITS copy of
+		// the scratch arrays and counters; what we write until we arrive goes to ours
 		const uint64_t tile_start = tile * (uint64_t) kTile;
 		uint32_t total = 0;
 		if constexpr (EXACT) {
@@ -395,13 +414,13 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	}
 	if (!tab_ready)
 		mbar_wait(tab_bar, 0); // a warp without a tile: the CTA must not retire under its own table copy
-	if (a.pdl && !waited)
-		pdl_wait(); // the previous scan is complete: the scratch arrays and the control block are ours now
 	em.finish();
 
 	// ---- per-CTA totals (shared memory)
 	if (lane == 0 && em.warp_count)
 		atomicAdd(s_count, em.warp_count);
+	if (em.lost && lane == 0)
+		atomicOr(s_bad, 4u);
 	if constexpr (kPacked) {
 		badacc &= 0xFCFCFCFCu;
 		if (__any_sync(kFull, badacc != 0) && lane == 0)
@@ -411,9 +430,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	if (threadIdx.x == 0)
 		trace_mark(a, 4);
 
-	// ---- order, part 1: exclusive prefix of the per-tile counts inside this CTA's span
+	// ---- order, part 1: exclusive prefix of the per-tile counts inside this CTA's span (in place: shared memory,
+	// and global memory for the tiles of a span too long for it)
 	const uint32_t G = gridDim.x;
-	if (a.want_positions) {
+	const unsigned long long my_total = *s_count;
+	if (a.want_positions && my_total) {
 		uint32_t carry = 0;
 		for (uint32_t base = 0; base < n_b; base += THREADS) {
 			const uint32_t i = base + threadIdx.x;
@@ -432,23 +453,21 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 					s_scan[32] = xi;
 			}
 			__syncthreads();
-			if (i < n_b)
-				a.tile_count[cta_lo + i] = carry + s_scan[warp] + incl - v;
+			if (i < n_b) {
+				const uint32_t excl = carry + s_scan[warp] + incl - v;
+				if (i < a.cnt_cap)
+					s_cnt[i] = excl;
+				else
+					a.tile_count[cta_lo + i] = excl;
+			}
 			carry += s_scan[32];
 			__syncthreads();
 		}
-		if (threadIdx.x == 0)
-			a.cta_total[blockIdx.x] = carry;
-		__syncthreads();
 	}
 
-	// ---- arrive: count + grid barrier + exit ticket + ordering slot in one atomic; the last CTA publishes.
-	// Who orders the staged matches: every CTA that arrives after the staging cursor has passed kSoloStage
-	// (the cursor only grows, and the CTA that reads it last reads its final value, so either somebody stays
-	// or at most kSoloStage slots are staged and the last CTA to arrive places them alone).  Everybody else
-	// retires at once: no grid-wide wait for a scan with few matches, its SMs go to the next scan of the stream.
+	// ---- publish: the CTA's total goes out first (the spans behind us wait for nothing else), then ONE atomic is
+	// count, arrival and exit ticket: the last CTA to arrive writes the result block.  Nobody waits for the grid.
 	bool publisher = false;
-	uint32_t *s_order = reinterpret_cast<uint32_t *>(smem + 48); // [0] orders?, [1] slot, [2] CTAs ordering
 	// the previous scan's counts have had a whole scan to arrive (the last one is collected by acwm_fetch_global_count)
 	auto collect_peers = [&]() {
 		if (a.xepoch < 2)
@@ -456,13 +475,15 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		a.ctl->result.global_count = collect_mailbox(a.peers[a.rank], a.world, a.xepoch - 1);
 		a.ctl->result.global_epoch = a.xepoch - 1;
 	};
+	const unsigned long long tag = (unsigned long long) ((a.epoch + 1u) & 0xffffffu) << kTotalShift;
 	if (threadIdx.x == 0) {
-		Work *other = &a.ctl->work[(a.epoch + 1u) & 1u];
-		if (blockIdx.x == 0) { // the successor launch's counters (its predecessor -- us -- is the only one that could still use them)
-			other->arrive = 0;
-			other->cursor = 0;
-			other->bad_text = 0;
-		}
+		if (a.want_positions)
+			atomicExch(a.cta_total + blockIdx.x, tag | my_total);
+		trace_mark(a, 5);
+		// overlap mode: from here on we touch what the previous scan of the stream publishes (result block,
+		// positions) -- and no CTA leaves before that scan is complete (the invariant behind Work)
+		if (a.pdl)
+			pdl_wait();
 		Result *res = &a.ctl->result;
 		unsigned long long old_count = 0, old_written = 0;
 		unsigned int old_bad = 0, old_ovf = 0;
@@ -474,24 +495,17 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		}
 		s_misc[1] = old_written;
 		if (*s_bad)
-			atomicOr(&wk->bad_text, 1u);
-		trace_mark(a, 5);
-		unsigned long long stay = 0;
-		if (a.want_positions)
-			stay = (!(a.tune & kTuneEarlyRetire) || __ldcg(&wk->cursor) > kSoloStage) ? 1ull : 0ull;
+			atomicOr(&wk->bad_text, *s_bad);
 		__threadfence();
-		const unsigned long long mine = *s_count;
-		const unsigned long long before = atomicAdd(&wk->arrive, (1ull << kArriveShift) + (stay << kStayShift) + mine);
+		const unsigned long long before = atomicAdd(&wk->arrive, (1ull << kArriveShift) + my_total);
 		trace_mark(a, 6);
-		const bool last = (before >> kArriveShift) == G - 1;
-		uint32_t order_slot = (uint32_t) (before >> kStayShift) & 0x1ffu; // CTAs that stay and arrived before us
-		uint32_t order_n = 0, orders = 0;
-		if (last) { // everybody has arrived: totals are final
+		if ((before >> kArriveShift) == G - 1) { // everybody has arrived: totals are final
 			__threadfence();
-			const unsigned long long cnt = (before & kArriveCountMask) + mine;
+			const unsigned long long cnt = (before & kArriveCountMask) + my_total;
 			const unsigned long long cur = __ldcg(&wk->cursor);
+			const unsigned int bad = __ldcg(&wk->bad_text);
 			unsigned long long r_written = old_written;
-			unsigned int r_ovf = old_ovf;
+			unsigned int r_ovf = old_ovf | ((bad >> 2) & 1u);
 			if (a.want_positions) {
 				if (old_written + cnt > a.cap || cur > a.stage_cap) {
 					r_ovf = 1;
@@ -501,7 +515,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			}
 			res->count = old_count + cnt;
 			res->written = r_written;
-			res->bad_text = old_bad | __ldcg(&wk->bad_text);
+			res->bad_text = old_bad | (bad & 3u);
 			res->overflow = r_ovf;
 			if (a.world > 1) { // hand this launch's count to every rank (ours included)
 				const unsigned long long tagged = ((unsigned long long) (a.xepoch & 0xffffu) << kMailShift) | cnt;
@@ -512,27 +526,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			} else
 				res->global_count = old_count + cnt;
 		}
-		if (a.want_positions) {
-			if (stay) {
-				unsigned long long v;
-				while (((v = ld_acquire_u64(&wk->arrive)) >> kArriveShift) < G)
-					__nanosleep(32);
-				__threadfence();
-				order_n = (uint32_t) (v >> kStayShift) & 0x1ffu;
-				orders = 1;
-			} else if (last && order_slot == 0) { // nobody stayed: at most kSoloStage slots, placed by this CTA alone
-				order_n = 1;
-				orders = 1;
-			}
-		}
-		s_order[0] = orders;
-		s_order[1] = order_slot;
-		s_order[2] = order_n;
-		trace_mark(a, 7);
 	}
-	if (a.want_positions)
-		__syncthreads();
-	if (!a.want_positions || !s_order[0]) {
+	if (!a.want_positions || !my_total) { // nothing of ours to place
 		if (threadIdx.x == 0)
 			trace_mark(a, 8);
 		if (publisher)
@@ -540,61 +535,69 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		return;
 	}
 
-	// ---- order, part 2: span bases = exclusive prefix of the per-CTA totals, then the scatter
-	unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_warps); // the ring buffers are free now
-	if (warp == 0) {
-		constexpr uint32_t kMaxChunks = 8; // grids of up to 256 CTAs in one batch of loads
-		unsigned long long v[kMaxChunks];
-#pragma unroll
-		for (uint32_t c = 0; c < kMaxChunks; c++) {
-			const uint32_t b = c * 32 + lane;
-			v[c] = b < G ? __ldcg(a.cta_total + b) : 0ull;
-		}
-		if (lane == 0)
-			s_misc[0] = __ldcg(&wk->cursor);
-		unsigned long long run = s_misc[1];
-#pragma unroll
-		for (uint32_t c = 0; c < kMaxChunks; c++) {
-			unsigned long long incl = v[c];
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const unsigned long long t = __shfl_up_sync(kFull, incl, d);
-				if ((int) lane >= d)
-					incl += t;
+	// ---- order, part 2: our span starts where the spans in front of us end (their totals: a look-back over
+	// at most G - 1 tagged words, normally all there already -- CTAs start in span order)
+	uint32_t *s_stall = reinterpret_cast<uint32_t *>(smem + 48);
+	if (warp == 1) { // not warp 0: its lane 0 may still be waiting for the previous scan
+		unsigned long long sum = 0;
+		bool stalled = false;
+		const unsigned long long t0 = globaltimer_ns();
+		for (uint32_t j = lane; j < blockIdx.x; j += 32) {
+			unsigned long long v;
+			uint32_t spins = 0;
+			while (((v = ld_acquire_u64(a.cta_total + j)) & ~kTotalMask) != tag) {
+				if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > kLookbackTimeoutNs) {
+					stalled = true;
+					break;
+				}
 			}
-			const uint32_t b = c * 32 + lane;
-			if (b < G)
-				s_base[b] = run + incl - v[c];
-			run += __shfl_sync(kFull, incl, 31);
+			if (stalled)
+				break;
+			sum += v & kTotalMask;
+		}
+#pragma unroll
+		for (int d = 16; d; d >>= 1)
+			sum += __shfl_xor_sync(kFull, sum, d);
+		stalled = __any_sync(kFull, stalled);
+		if (lane == 0) {
+			s_misc[0] = sum;
+			*s_stall = stalled ? 1u : 0u;
+			if (stalled) // positions of this scan are incomplete: acwm_fetch reports it
+				atomicMax(&a.ctl->result.order_failed, a.epoch + 1u);
 		}
 	}
-	__syncthreads();
-	const unsigned long long cursor = s_misc[0];
-	const uint64_t staged = cursor < a.stage_cap ? cursor : a.stage_cap;
-	const uint64_t stride = (uint64_t) s_order[2] * THREADS;
-	constexpr int kBatch = 4; // staged entries in flight per thread (the lone CTA of a sparse scan places up to kSoloStage of them)
-	for (uint64_t i0 = (uint64_t) s_order[1] * THREADS + threadIdx.x; i0 < staged; i0 += kBatch * stride) {
-		uint64_t e[kBatch];
-		uint32_t tc[kBatch];
+	__syncthreads(); // also: thread 0 has passed its wait for the previous scan, s_misc[1] is set
+	if (threadIdx.x == 0)
+		trace_mark(a, 7);
+	if (!*s_stall) {
+		const unsigned long long span_base = s_misc[1] + s_misc[0];
+		// every warp moves what it staged: entry -> positions[span base + tile offset + rank]
+		constexpr int kBatch = 4;
+		for (uint32_t d = 0; d < em.n_log; d++) {
+			const unsigned long long desc = em.log[d];
+			const unsigned long long ptr = desc & ((1ull << 40) - 1);
+			const uint32_t len = (uint32_t) (desc >> 40);
+			for (uint32_t i0 = lane; i0 < len; i0 += 32 * kBatch) {
+				uint64_t e[kBatch];
 #pragma unroll
-		for (int u = 0; u < kBatch; u++) {
-			const uint64_t i = i0 + (uint64_t) u * stride;
-			e[u] = i < staged ? __ldcg(a.staging + i) : ~0ull; // all-ones: unused tail of a warp's reservation
-		}
+				for (int u = 0; u < kBatch; u++) {
+					const uint32_t i = i0 + 32 * u;
+					e[u] = (i < len && ptr + i < a.stage_cap) ? __ldcg(a.staging + ptr + i) : ~0ull;
+				}
 #pragma unroll
-		for (int u = 0; u < kBatch; u++)
-			tc[u] = e[u] != ~0ull ? __ldcg(a.tile_count + (e[u] >> (kRankBits + kPosBits))) : 0u;
-#pragma unroll
-		for (int u = 0; u < kBatch; u++) {
-			if (e[u] == ~0ull)
-				continue;
-			const uint64_t tile = e[u] >> (kRankBits + kPosBits);
-			const uint32_t rank = (uint32_t) (e[u] >> kPosBits) & ((1u << kRankBits) - 1);
-			const uint32_t pos = (uint32_t) e[u] & ((1u << kPosBits) - 1);
-			const uint64_t owner = (tile - a.tile_lo) / a.tiles_per_cta;
-			const uint64_t at = s_base[owner] + tc[u] + rank;
-			if (at < a.cap)
-				a.positions[at] = tile * kTile + pos - a.data_lo;
+				for (int u = 0; u < kBatch; u++) {
+					if (e[u] == ~0ull)
+						continue;
+					const uint64_t tile = e[u] >> (kRankBits + kPosBits);
+					const uint32_t rank = (uint32_t) (e[u] >> kPosBits) & ((1u << kRankBits) - 1);
+					const uint32_t pos = (uint32_t) e[u] & ((1u << kPosBits) - 1);
+					const uint64_t ti = tile - cta_lo;
+					const uint32_t off = ti < a.cnt_cap ? s_cnt[ti] : __ldcg(a.tile_count + tile);
+					const unsigned long long at = span_base + off + rank;
+					if (at < a.cap)
+						a.positions[at] = tile * kTile + pos - a.data_lo;
+				}
+			}
 		}
 	}
 	if (threadIdx.x == 0)

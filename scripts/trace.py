@@ -49,8 +49,8 @@ def log(s=""):
     out.write(s + "\n")
 
 
-names = ["entry", "prologue done", "first TMAs issued", "tables ready (warp 0)", "all warps done (sync)",
-         "span prefix done", "arrived", "role known / grid wait done", "exit"]
+names = ["entry", "first copies issued", "CTA set up", "tables ready (warp 0)", "all warps done (sync)",
+         "span total published", "arrived", "look-back done", "exit"]
 t0 = T[0, :, 0].min()
 log(f"# {wl} {mode}: {NL} consecutive launches, 148 CTAs; times in us relative to the first CTA entry of launch 0")
 for k in range(NL):
@@ -63,6 +63,7 @@ log("per-CTA phase durations (us), median / p10 / p90 / max over CTAs, averaged 
 for a_, b_ in ((0, 1), (1, 2), (2, 3), (0, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (0, 8)):
     d = (T[2:, :, b_] - T[2:, :, a_]) / 1e3
     log(f"  {names[a_]:>28s} -> {names[b_]:<28s} med {np.median(d):7.2f}  p10 {np.percentile(d,10):7.2f}  p90 {np.percentile(d,90):7.2f}  max {d.max():7.2f}")
+log(f"  cost of one stamp (two back-to-back pairs): {np.median(T[2:, :, 9] - T[2:, :, 2])/1e3:.2f} {np.median(T[2:, :, 10] - T[2:, :, 9])/1e3:.2f}")
 first = (T[2:, :, 16:48] - T[2:, :, 0:1]) / 1e3
 end = (T[2:, :, 48:80] - T[2:, :, 0:1]) / 1e3
 tiles = T[2:, :, 80:112]
