@@ -35,7 +35,8 @@ constexpr uint32_t kSmemReserve = 1024;             // CTA-level scratch (barrie
 
 // Staging entry: [tile:28 | rank:22 | pos_in_tile:14]
 constexpr uint32_t kPosBits = 14, kRankBits = 22;
-constexpr uint32_t kStageBlock = 32;                // staging slots of a warp's first reservation (each further one doubles)
+constexpr uint32_t kStageBlockLog2 = 7;
+constexpr uint32_t kStageBlock = 1u << kStageBlockLog2; // staging slots of a warp's first reservation (each further one doubles)
 
 // (warps, stages) the scan kernel is launched with, in order of preference.  The 2-bit path
 // copies a tile into registers first and refills its slot while it walks, so one slot per

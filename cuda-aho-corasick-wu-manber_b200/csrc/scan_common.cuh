@@ -217,7 +217,7 @@ struct Emitter {
 		new_ptr = 0;
 		if (total > blk_left) {
 			const uint32_t extra = total - blk_left;
-			const uint32_t grab = max(extra, kStageBlock << min(n_log, kMaxGrabLog2 - 5u));
+			const uint32_t grab = max(extra, kStageBlock << min(n_log, kMaxGrabLog2 - kStageBlockLog2));
 			unsigned long long p = 0;
 			if (lane_id() == 0) {
 				p = atomicAdd(&wk->cursor, (unsigned long long) grab);

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 			idx = atomicAdd(s_next, 1u);
 		issue(s, __shfl_sync(kFull, idx, 0));
 	};
+#pragma unroll 1 // cold code, once per CTA: keep it small
 	for (uint32_t s = 0; s < stages; s++)
 		issue(s, s * W + warp);
 
@@ -154,10 +155,13 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		if (tab_bytes) {
 			const uint64_t keep = policy_evict_last();
 			mbar_expect_tx(tab_bar, tab_bytes);
+#pragma unroll 1
 			for (uint32_t off = 0; off < front_smem; off += 16384)
 				tma_bulk_g2s(s_front + off, a.front + off, min(16384u, front_smem - off), tab_bar, keep);
+#pragma unroll 1
 			for (uint32_t off = 0; off < rm_bytes; off += 16384)
 				tma_bulk_g2s(s_rmask + off, a.rmask + off, min(16384u, rm_bytes - off), tab_bar, keep);
+#pragma unroll 1
 			for (uint32_t off = 0; off < f2_bytes; off += 16384)
 				tma_bulk_g2s(reinterpret_cast<uint8_t *>(s_f2) + off, reinterpret_cast<const uint8_t *>(a.filter2) + off,
 						min(16384u, f2_bytes - off), tab_bar, keep);
@@ -435,33 +439,33 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	const uint32_t G = gridDim.x;
 	const unsigned long long my_total = *s_count;
 	if (a.want_positions && my_total) {
-		uint32_t carry = 0;
-		for (uint32_t base = 0; base < n_b; base += THREADS) {
-			const uint32_t i = base + threadIdx.x;
-			uint32_t v = 0;
-			if (i < n_b)
-				v = i < a.cnt_cap ? s_cnt[i] : __ldcg(a.tile_count + cta_lo + i);
-			const uint32_t incl = warp_incl_scan(v);
-			if (lane == 31)
-				s_scan[warp] = incl;
-			__syncthreads();
-			if (warp == 0) {
-				const uint32_t x = lane < W ? s_scan[lane] : 0u;
-				const uint32_t xi = warp_incl_scan(x);
-				s_scan[lane] = xi - x;
-				if (lane == 31)
-					s_scan[32] = xi;
+		if (warp == 0) { // one warp, 8 tiles per lane and pass: no block-wide barrier inside
+			uint32_t carry = 0;
+			for (uint32_t base = 0; base < n_b; base += 256) {
+				uint32_t v[8], sum = 0;
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const uint32_t i = base + lane * 8 + k;
+					v[k] = 0;
+					if (i < n_b)
+						v[k] = i < a.cnt_cap ? s_cnt[i] : __ldcg(a.tile_count + cta_lo + i);
+					sum += v[k];
+				}
+				const uint32_t incl = warp_incl_scan(sum);
+				uint32_t run = carry + incl - sum;
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const uint32_t i = base + lane * 8 + k;
+					if (i < n_b) {
+						if (i < a.cnt_cap)
+							s_cnt[i] = run;
+						else
+							a.tile_count[cta_lo + i] = run;
+					}
+					run += v[k];
+				}
+				carry += __shfl_sync(kFull, incl, 31);
 			}
-			__syncthreads();
-			if (i < n_b) {
-				const uint32_t excl = carry + s_scan[warp] + incl - v;
-				if (i < a.cnt_cap)
-					s_cnt[i] = excl;
-				else
-					a.tile_count[cta_lo + i] = excl;
-			}
-			carry += s_scan[32];
-			__syncthreads();
 		}
 	}
 
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	const unsigned long long tag = (unsigned long long) ((a.epoch + 1u) & 0xffffffu) << kTotalShift;
 	if (threadIdx.x == 0) {
 		if (a.want_positions)
-			atomicExch(a.cta_total + blockIdx.x, tag | my_total);
+			__stcg(a.cta_total + blockIdx.x, tag | my_total); // one 8-byte word: tag and value arrive together
 		trace_mark(a, 5);
 		// overlap mode: from here on we touch what the previous scan of the stream publishes (result block,
 		// positions) -- and no CTA leaves before that scan is complete (the invariant behind Work)

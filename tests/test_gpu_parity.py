@@ -142,6 +142,35 @@ def test_overlapped_back_to_back_scans(acwm, oracle, torch_cuda):
         mt.close()
 
 
+@pytest.mark.parametrize("threads", [0, 128])
+@pytest.mark.parametrize("algo_name", ["AC", "WM"])
+def test_dense_matches_back_to_back(acwm, oracle, torch_cuda, threads, algo_name):
+    """Match-dense text (1 position in 20 matches; then every position): the warps' staging reservations double
+    and straddle blocks, every CTA places its own matches behind a look-back over the spans in front of it, and
+    consecutive launches overlap -- count and positions still equal the oracle's."""
+    torch = torch_cuda
+    dg = __import__("acwm_pkg").submodule("datagen")
+    rng = np.random.default_rng(5)
+    n = 24 << 20
+    texts = [dg.text_host(n, 4, 31), dg.text_host(n - 777, 4, 32)]
+    all4 = np.array([[(v >> (2 * k)) & 3 for k in range(4)] for v in range(256)], np.uint8)
+    for pats in (all4[rng.choice(256, 13, replace=False)], all4):
+        refs = [oracle.set_search(pats, t) for t in texts]
+        d = [torch.from_numpy(t).cuda() for t in texts]
+        opts = dict(force_threads=threads) if threads else {}
+        mt = acwm.Matcher(acwm.AC if algo_name == "AC" else acwm.WM, pats, 4, **opts).upload(pos_capacity=n)
+        mt.set_overlap(True)
+        st = torch.cuda.current_stream().cuda_stream
+        for last in (0, 1, 0):
+            for k in range(3):  # no synchronisation between the launches
+                mt.scan_tensor(d[(last + k + 1) % 2])
+            mt.scan_tensor(d[last])
+            count, pos, _ = mt.fetch(cap=n, stream=st)
+            assert count == refs[last]["count"], (algo_name, threads, len(pats), last)
+            assert np.array_equal(pos, refs[last]["positions"]), (algo_name, threads, len(pats), last)
+        mt.close()
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_sharded_scans_sum_to_whole(acwm, oracle, torch_cuda, world):
     """The multi-GPU geometry run on one GPU: shard scans are exactly-once."""
