@@ -87,6 +87,8 @@ def lib():
         L.acwm_search_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p, C.c_void_p, C.c_uint64, _u64p]
         L.acwm_last_kernel_seconds.restype = C.c_double
         L.acwm_last_kernel_seconds.argtypes = [C.c_void_p]
+        L.acwm_last_h2d_bytes.restype = C.c_uint64
+        L.acwm_last_h2d_bytes.argtypes = [C.c_void_p]
         L.acwm_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.acwm_set_overlap.argtypes = [C.c_void_p, C.c_int]
         L.acwm_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, _u64p]
@@ -101,6 +103,7 @@ def lib():
         L.acwm_shard_bounds.restype = None
         L.acwm_table_blob.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _u64p]
         L.acwm_set_trace.argtypes = [C.c_void_p, C.c_void_p]
+        L.acwm_pack_text_2bit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_int)]
         L.acwm_trace_words_per_cta.restype = C.c_uint32
         L.acwm_symbol_map.argtypes = [C.c_uint32, _u8p]
         L.acwm_encode_symbols.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, _u64p]
@@ -270,6 +273,11 @@ class Matcher:
         return float(lib().acwm_last_kernel_seconds(self._h))
 
     @property
+    def last_h2d_bytes(self) -> int:
+        """Bytes of text the last search_host sent over the link (n, or n/4 when the host packer ran)."""
+        return int(lib().acwm_last_h2d_bytes(self._h))
+
+    @property
     def launch_count(self) -> int:
         return int(lib().acwm_launch_count(self._h))
 
@@ -314,3 +322,12 @@ def select_data_file(m: int, n: int, alphabet: int, data_root: str | None = None
     pp, tp = C.create_string_buffer(4096), C.create_string_buffer(4096)
     _check(lib().acwm_select_data_file(m, n, alphabet, os.fsencode(data_root) if data_root else None, pp, tp, 4096))
     return os.fsdecode(pp.value), os.fsdecode(tp.value)
+
+
+def pack_text_2bit(text: np.ndarray):
+    """(packed uint8[ceil(n/4)], bad_text) -- the host-side packer of acwm_search_host (see acwm_pack_text_2bit)."""
+    text = np.ascontiguousarray(text, np.uint8)
+    out = np.empty((text.size + 3) // 4, np.uint8)
+    bad = C.c_int()
+    _check(lib().acwm_pack_text_2bit(C.c_void_p(text.ctypes.data), text.size, C.c_void_p(out.ctypes.data), C.byref(bad)))
+    return out, bool(bad.value)

@@ -6,15 +6,20 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <mutex>
 #include <string>
 #include <vector>
 
+#include "hostpack.hpp"
 #include "matcher.hpp"
 
 namespace acwm {
 
 cudaError_t launch_scan_packed(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st);
 cudaError_t launch_scan_bytes(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st);
+
+constexpr uint64_t kBounceEntries = 8192; // positions fetched together with the result block
 
 static thread_local std::string g_last_error;
 
@@ -117,6 +122,7 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	CU(cudaMalloc((void **) &mt->d_ctl, sizeof(Control)));
 	CU(cudaMemset(mt->d_ctl, 0, sizeof(Control)));
 	CU(cudaMallocHost((void **) &mt->h_res, sizeof(Result)));
+	CU(cudaMallocHost((void **) &mt->h_bounce, kBounceEntries * 8));
 	CU(cudaMalloc((void **) &mt->d_cta_total, 2 * kMaxScanBlocks * sizeof(unsigned long long)));
 	CU(cudaStreamCreateWithFlags(&mt->s_copy, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&mt->s_scan, cudaStreamNonBlocking));
@@ -163,7 +169,7 @@ static uint32_t kernel_tune() {
 // Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
 // cooperative kernel that scans, orders the positions and publishes the result block.
 static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
-		uint64_t tile_hi, int want_positions, int append, int exchange, cudaStream_t st) {
+		uint64_t tile_hi, int want_positions, int append, int exchange, cudaStream_t st, int packed_in = 0) {
 	const Compiled &c = mt->c;
 	ScanArgs a;
 	memset(&a, 0, sizeof(a));
@@ -196,6 +202,7 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.want_positions = want_positions;
 	a.append = append;
 	a.tune = kernel_tune();
+	a.packed_in = packed_in ? 1u : 0u;
 	a.trace = mt->d_trace;
 	if (exchange && mt->peer_world > 1) {
 		a.world = mt->peer_world;
@@ -232,6 +239,130 @@ __global__ void collect_last_kernel(Control *ctl, const unsigned long long *box,
 		ctl->result.global_count = collect_mailbox(box, world, x);
 		ctl->result.global_epoch = x;
 	}
+}
+
+// Host text of a 2-bit matcher (alphabet <= 4): the host cores pack it 4 symbols per byte into a ring of pinned
+// buffers (hostpack.cpp), a quarter of the bytes crosses PCIe, and the scan takes the packed tiles as they are.
+// The packer threads run ahead through the text; this thread takes the chunks in order (and packs along while it
+// waits), sends each one and launches its scan.
+constexpr uint64_t kHostPackMin = 4ull << 20;
+constexpr unsigned kHostPackMinThreads = 10;
+constexpr uint64_t kPackChunk = 56 * HostPacker::kPieceSymbols; // 14 Mi symbols = 4096 tiles = 56 work items
+constexpr unsigned kPackRing = 16;
+static_assert(kPackChunk % kTile == 0 && kPackChunk % 64 == 0, "chunks are whole tiles and whole 16-byte pieces");
+// ACWM_HOST_PACK: 0 = never, 2 = always (tests), unset / 1 = when the host has the cores for it
+static int host_pack_mode() {
+	const char *e = getenv("ACWM_HOST_PACK");
+	return e && *e ? atoi(e) : 1;
+}
+
+static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t *count, uint64_t *positions,
+		uint64_t cap, uint64_t *n_written, int want_positions) {
+	int rc;
+	const uint64_t T = kTile;
+	const uint64_t n_tiles = (n + T - 1) / T;
+	const uint64_t packed_total = ((n + 63) / 64) * 16; // zero-padded to whole 16-byte pieces
+	if (packed_total + 64 > mt->text_cap) {
+		if (mt->d_text)
+			cudaFree(mt->d_text);
+		mt->d_text = nullptr;
+		mt->text_cap = 0;
+		CU(cudaMalloc((void **) &mt->d_text, packed_total + 64));
+		mt->text_cap = packed_total + 64;
+	}
+	if (want_positions && (rc = ensure_tiles(mt, n_tiles)))
+		return rc;
+	const uint64_t chunk_tiles = kPackChunk / T, slot_bytes = kPackChunk / 4 + 64;
+	const uint64_t n_chunks = std::max<uint64_t>(1, (n + kPackChunk - 1) / kPackChunk);
+	if (!mt->h_pack_ring) {
+		CU(cudaMallocHost((void **) &mt->h_pack_ring, kPackRing * slot_bytes));
+		for (auto &e : mt->ev_pack)
+			CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	while (mt->ev_time.size() < 2 * n_chunks) {
+		cudaEvent_t e;
+		CU(cudaEventCreate(&e));
+		mt->ev_time.push_back(e);
+	}
+	apply_l2_window(mt, mt->s_scan);
+	mt->first_epoch = mt->epoch;
+	static const bool dbg = getenv("ACWM_DEBUG_TIMING") != nullptr;
+	auto now = [] {
+		timespec ts;
+		clock_gettime(CLOCK_MONOTONIC, &ts);
+		return ts.tv_sec + 1e-9 * ts.tv_nsec;
+	};
+	const double t_begin = now();
+	double t_wait = 0;
+	std::vector<double> t_issued;
+	HostPacker &pk = *mt->packer;
+	struct Release { // error returns too
+		HostPacker &p;
+		~Release() { p.finish(); }
+	} release{pk};
+	pk.begin(text, n, kPackChunk, mt->h_pack_ring, slot_bytes, kPackRing);
+	uint64_t oldest = 0; // first chunk whose copy is not known to be complete (its ring slot is still taken)
+	for (uint64_t ci = 0; ci < n_chunks; ci++) {
+		const uint64_t b0 = std::min<uint64_t>(n, ci * kPackChunk), b1 = std::min<uint64_t>(n, (ci + 1) * kPackChunk);
+		while (ci >= oldest + kPackRing) { // the packers may not start this chunk before its slot is free
+			CU(cudaEventSynchronize(mt->ev_pack[oldest % kPackRing]));
+			pk.recycle(oldest++);
+		}
+		const double t0 = now();
+		pk.wait_chunk(ci);
+		t_wait += now() - t0;
+		uint8_t *slot = mt->h_pack_ring + (ci % kPackRing) * slot_bytes;
+		const uint64_t used = (b1 - b0 + 3) / 4, bytes = ((b1 - b0 + 63) / 64) * 16;
+		if (bytes > used)
+			memset(slot + used, 0, bytes - used); // the last piece of the text: zero padding
+		if (dbg)
+			t_issued.push_back((now() - t_begin) * 1e3);
+		if (bytes)
+			CU(cudaMemcpyAsync(mt->d_text + b0 / 4, slot, bytes, cudaMemcpyHostToDevice, mt->s_copy));
+		cudaEvent_t ev = mt->ev_pack[ci % kPackRing];
+		CU(cudaEventRecord(ev, mt->s_copy));
+		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
+		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
+		if ((rc = launch_scan(mt, mt->d_text, n, 0, std::min(n_tiles, ci * chunk_tiles),
+					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, 0, mt->s_scan, 1)))
+			return rc;
+		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
+		while (oldest < ci && cudaEventQuery(mt->ev_pack[oldest % kPackRing]) == cudaSuccess)
+			pk.recycle(oldest++); // let the packers run further ahead
+	}
+	(void) cudaGetLastError(); // cudaEventQuery's cudaErrorNotReady is not an error
+	const uint64_t bad = pk.bad();
+	mt->last_h2d_bytes = packed_total;
+	mt->last_want_positions = want_positions;
+	const double t_issue = now();
+	rc = acwm_fetch(mt, count, positions, cap, n_written, mt->s_scan);
+	pk.finish();
+	double secs = 0;
+	for (uint64_t ci = 0; ci < n_chunks; ci++) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, mt->ev_time[2 * ci], mt->ev_time[2 * ci + 1]) == cudaSuccess)
+			secs += ms * 1e-3;
+	}
+	mt->last_kernel_s = secs;
+	if (dbg) {
+		fprintf(stderr, "  copy of chunk i issued at (ms after the call):");
+		for (double t : t_issued)
+			fprintf(stderr, " %.3f", t);
+		fprintf(stderr, "\n  scan of chunk i done at (ms after the first chunk had landed):");
+		for (uint64_t ci = 0; ci < n_chunks; ci++) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, mt->ev_time[0], mt->ev_time[2 * ci + 1]);
+			fprintf(stderr, " %.3f", ms);
+		}
+		fprintf(stderr, "\n");
+	}
+	if (dbg)
+		fprintf(stderr, "acwm host-packed search: n %llu, %llu chunks, %u threads: waited for the packers %.3f ms, issue loop %.3f ms, fetch %.3f ms, kernels %.3f ms\n",
+				(unsigned long long) n, (unsigned long long) n_chunks, pk.threads(), t_wait * 1e3, (t_issue - t_begin) * 1e3,
+				(now() - t_issue) * 1e3, secs * 1e3);
+	if (bad & 0xFCFCFCFCFCFCFCFCull)
+		return set_error(ACWM_ERR_BAD_TEXT, "text holds a byte >= 4 but the matcher was built for alphabet <= 4");
+	return rc;
 }
 
 } // namespace acwm
@@ -312,8 +443,18 @@ int acwm_fetch(acwm_matcher *mt, uint64_t *count, uint64_t *positions, uint64_t 
 	if (!mt || !mt->uploaded)
 		return set_error(ACWM_ERR_INVALID, "matcher not uploaded");
 	cudaStream_t st = (cudaStream_t) stream;
+	static const bool dbg = getenv("ACWM_DEBUG_TIMING") != nullptr;
+	timespec ts0, ts1;
+	clock_gettime(CLOCK_MONOTONIC, &ts0);
 	CU(cudaMemcpyAsync(mt->h_res, &mt->d_ctl->result, sizeof(Result), cudaMemcpyDeviceToHost, st));
+	// the first positions ride along (pinned bounce buffer): a sparse result needs no second round trip
+	const uint64_t spec = (positions && mt->last_want_positions) ? std::min<uint64_t>({cap, mt->pos_cap, kBounceEntries}) : 0;
+	if (spec)
+		CU(cudaMemcpyAsync(mt->h_bounce, mt->d_positions, spec * 8, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	clock_gettime(CLOCK_MONOTONIC, &ts1);
+	if (dbg)
+		fprintf(stderr, "  acwm_fetch: result block after %.3f ms\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
 	const Result &h = *mt->h_res;
 	if (count)
 		*count = h.count;
@@ -326,8 +467,16 @@ int acwm_fetch(acwm_matcher *mt, uint64_t *count, uint64_t *positions, uint64_t 
 	if (positions && mt->last_want_positions) {
 		const uint64_t have = std::min<uint64_t>(h.written, mt->pos_cap);
 		const uint64_t w = std::min<uint64_t>(have, cap);
-		if (w)
-			CU(cudaMemcpy(positions, mt->d_positions, w * 8, cudaMemcpyDeviceToHost));
+		const uint64_t have_b = std::min(w, spec);
+		if (have_b)
+			memcpy(positions, mt->h_bounce, have_b * 8);
+		if (w > have_b)
+			CU(cudaMemcpy(positions + have_b, mt->d_positions + have_b, (w - have_b) * 8, cudaMemcpyDeviceToHost));
+		if (dbg) {
+			clock_gettime(CLOCK_MONOTONIC, &ts0);
+			fprintf(stderr, "  acwm_fetch: %llu positions after another %.3f ms\n", (unsigned long long) w,
+					(ts0.tv_sec - ts1.tv_sec) * 1e3 + (ts0.tv_nsec - ts1.tv_nsec) * 1e-6);
+		}
 		if (n_written)
 			*n_written = w;
 		if (h.overflow || h.count > cap)
@@ -357,6 +506,14 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 	const int want_positions = positions != nullptr && cap > 0;
 	if (want_positions && (rc = ensure_positions(mt, cap)))
 		return rc;
+	const int pack_mode = host_pack_mode();
+	if (mt->c.prm.packed2bit && n >= kHostPackMin && pack_mode > 0) {
+		if (!mt->packer)
+			mt->packer = new HostPacker();
+		// worth it only with enough cores to out-run the link (a core packs 5-7 GB/s, PCIe moves ~50 GB/s of raw text)
+		if (mt->packer->threads() >= kHostPackMinThreads || pack_mode == 2)
+			return search_host_packed(mt, text, n, count, positions, cap, n_written, want_positions);
+	}
 	if (n + 64 > mt->text_cap) {
 		if (mt->d_text)
 			cudaFree(mt->d_text);
@@ -395,6 +552,7 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
 	}
 	mt->last_want_positions = want_positions;
+	mt->last_h2d_bytes = n;
 	rc = acwm_fetch(mt, count, positions, cap, n_written, mt->s_scan);
 	double secs = 0;
 	for (uint64_t ci = 0; ci < n_chunks; ci++) {
@@ -407,6 +565,19 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 }
 
 double acwm_last_kernel_seconds(const acwm_matcher *mt) { return mt ? mt->last_kernel_s : 0.0; }
+uint64_t acwm_last_h2d_bytes(const acwm_matcher *mt) { return mt ? mt->last_h2d_bytes : 0; }
+
+int acwm_pack_text_2bit(const uint8_t *text, uint64_t n, uint8_t *packed, int *bad_text) {
+	if ((!text && n) || !packed)
+		return set_error(ACWM_ERR_INVALID, "NULL argument");
+	static HostPacker pool; // shared by callers of this entry point; matchers own theirs
+	static std::mutex mu;
+	std::lock_guard<std::mutex> g(mu);
+	const uint64_t bad = pool.pack(text, packed, n);
+	if (bad_text)
+		*bad_text = (bad & 0xFCFCFCFCFCFCFCFCull) != 0;
+	return ACWM_OK;
+}
 
 int acwm_set_overlap(acwm_matcher *mt, int on) {
 	if (!mt)
@@ -507,6 +678,13 @@ void acwm_free(acwm_matcher *mt) {
 			cudaFree(mt->d_text);
 		if (mt->h_res)
 			cudaFreeHost(mt->h_res);
+		if (mt->h_bounce)
+			cudaFreeHost(mt->h_bounce);
+		if (mt->h_pack_ring)
+			cudaFreeHost(mt->h_pack_ring);
+		for (auto e : mt->ev_pack)
+			if (e)
+				cudaEventDestroy(e);
 		if (mt->s_copy)
 			cudaStreamDestroy(mt->s_copy);
 		if (mt->s_scan)
@@ -521,6 +699,7 @@ void acwm_free(acwm_matcher *mt) {
 				cudaEventDestroy(e);
 		(void) cudaGetLastError();
 	}
+	delete mt->packer;
 	delete mt;
 }
 

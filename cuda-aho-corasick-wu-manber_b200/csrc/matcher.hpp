@@ -12,6 +12,7 @@
 namespace acwm {
 
 constexpr uint32_t kMaxScanBlocks = 4096;
+class HostPacker;
 
 int set_error(int code, const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
@@ -38,6 +39,7 @@ struct acwm_matcher {
 	uint8_t *d_patterns = nullptr;
 	acwm::Control *d_ctl = nullptr;
 	acwm::Result *h_res = nullptr;
+	uint64_t *h_bounce = nullptr; // pinned: the first positions of a result
 	uint64_t *d_staging = nullptr, *d_positions = nullptr;
 	uint64_t pos_cap = 0, stage_cap = 0;
 	uint32_t *d_tile_count = nullptr;
@@ -48,6 +50,9 @@ struct acwm_matcher {
 	uint64_t text_cap = 0;
 	cudaStream_t s_copy = nullptr, s_scan = nullptr;
 	std::array<cudaEvent_t, 4> ev_copy{};
+	acwm::HostPacker *packer = nullptr;      // 2-bit host packer (alphabet <= 4 host texts), created on first use
+	uint8_t *h_pack_ring = nullptr;          // pinned ring the packer writes and the H2D copies read
+	std::array<cudaEvent_t, 16> ev_pack{};    // one per ring slot: its copy is done
 	std::vector<cudaEvent_t> ev_time;
 	std::array<cudaEvent_t, 2> ev_prof{};
 	bool profiling = false;
@@ -59,6 +64,7 @@ struct acwm_matcher {
 	uint32_t peer_world = 0, peer_rank = 0, xepoch = 0;
 	uint64_t peer_ptrs[acwm::kMaxPeers] = {};
 	double last_kernel_s = 0;
+	uint64_t last_h2d_bytes = 0; // bytes of text the last acwm_search_host sent over the link
 	int last_want_positions = 0;
 	unsigned long long launches = 0;
 };

@@ -42,7 +42,7 @@ struct BytesKey {
 // with the 16 bytes in front of it
 #define ACWM_SCAN_GROUPS()                                         \
 	const uint8_t *chunk;                                          \
-	__device__ __forceinline__ void load(const ScanArgs &, const uint8_t *c, uint32_t *, uint32_t &) { chunk = c; } \
+	__device__ __forceinline__ void load(const ScanArgs &, const uint8_t *buf, uint32_t *, uint32_t &) { chunk = buf + kHalo + lane_id() * kLane; } \
 	__device__ __forceinline__ void walk(const ScanArgs &a) {      \
 		begin(a, chunk);                                           \
 		uint4 prev = *reinterpret_cast<const uint4 *>(chunk - 16); \

@@ -81,6 +81,8 @@ struct ScanArgs {
 	int append;                  // 1: add to ctl->result instead of replacing it (chunked host text)
 	int pdl;                     // 1: launched as a programmatic dependent launch (consecutive scans may overlap)
 	uint32_t tune;               // kTune* bits
+	uint32_t packed_in;          // 1: text16 holds the text already packed 4 symbols per byte (host-side packer of
+	                             // acwm_search_host, alphabet <= 4): data_lo = 0, buffer zero-padded to 16 bytes
 	unsigned long long *trace;   // instrumentation (acwm_set_trace): kTraceWords of %globaltimer stamps per CTA, else NULL
 };
 
@@ -276,13 +278,22 @@ __device__ __forceinline__ uint32_t verify_window(const ScanArgs &a, uint32_t ke
 			continue; // window would start before the text / end after it / not ours to report
 		bool ok = true;
 		if (!(en.len >> 31)) {
-			const uint8_t *t = a.text16 + (e + 1 - len);
 			const uint8_t *q = a.patterns + en.offset;
-			for (uint32_t k = 0; k < len; k++)
-				if (t[k] != q[k]) {
-					ok = false;
-					break;
-				}
+			if (a.packed_in) {
+				const uint64_t s0 = e + 1 - len;
+				for (uint32_t k = 0; k < len; k++)
+					if (((a.text16[(s0 + k) >> 2] >> (2 * ((s0 + k) & 3))) & 3u) != q[k]) {
+						ok = false;
+						break;
+					}
+			} else {
+				const uint8_t *t = a.text16 + (e + 1 - len);
+				for (uint32_t k = 0; k < len; k++)
+					if (t[k] != q[k]) {
+						ok = false;
+						break;
+					}
+			}
 		}
 		mult += ok;
 	}

@@ -53,7 +53,24 @@ static __device__ __noinline__ void load_tile_edge(const ScanArgs &a, uint64_t t
 	asm volatile("cp.async.wait_all;" ::: "memory"); // the caller's __syncwarp publishes the tile to the warp
 }
 
+// Pre-packed text (4 symbols per byte, ScanArgs.packed_in): the slot receives [16 bytes of history][896 bytes of
+// tile]; the device buffer is zero-padded to a multiple of 16 bytes, so only the first tile needs care.
+static __device__ __noinline__ void load_tile_edge_packed(const ScanArgs &a, uint64_t tile, uint8_t *buf) {
+	const long long base = (long long) (tile * (uint64_t) (kTile / 4)) - (long long) (kHalo / 4);
+	const long long end = (long long) (((a.data_hi + 63) & ~(uint64_t) 63) / 4);
+	for (int c = (int) lane_id(); c < (int) (kLoadBytes / 4 / 16); c += 32) {
+		const long long off = base + 16ll * c;
+		if (off >= 0 && off + 16 <= end)
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(buf + 16 * c)), "l"(a.text16 + off) : "memory");
+		else
+			*reinterpret_cast<uint4 *>(buf + 16 * c) = make_uint4(0, 0, 0, 0);
+	}
+	asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 __device__ __forceinline__ bool tile_is_interior(const ScanArgs &a, uint64_t tile) {
+	if (a.packed_in)
+		return tile >= 1 && (tile + 1) * (uint64_t) kTile <= ((a.data_hi + 63) & ~(uint64_t) 63);
 	return tile >= 1 && (tile + 1) * (uint64_t) kTile <= (a.data_hi & ~(uint64_t) 15);
 }
 
@@ -130,12 +147,20 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 				// the generic-proxy reads of this slot are done (__syncwarp before us): order
 				// them before the async-proxy write
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				mbar_expect_tx(&bars[s], kLoadBytes);
-				tma_bulk_g2s(dst, a.text16 + t * (uint64_t) kTile - kHalo, kLoadBytes, &bars[s], stream_pol);
+				if (kPacked && a.packed_in) {
+					mbar_expect_tx(&bars[s], kLoadBytes / 4);
+					tma_bulk_g2s(dst, a.text16 + t * (uint64_t) (kTile / 4) - kHalo / 4, kLoadBytes / 4, &bars[s], stream_pol);
+				} else {
+					mbar_expect_tx(&bars[s], kLoadBytes);
+					tma_bulk_g2s(dst, a.text16 + t * (uint64_t) kTile - kHalo, kLoadBytes, &bars[s], stream_pol);
+				}
 			}
 			tma_mask |= 1u << s;
 		} else {
-			load_tile_edge(a, t, dst);
+			if (kPacked && a.packed_in)
+				load_tile_edge_packed(a, t, dst);
+			else
+				load_tile_edge(a, t, dst);
 			tma_mask &= ~(1u << s);
 		}
 	};
@@ -217,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		__syncwarp();
 
 		const uint8_t *buf = bufs + slot * kBufBytes;
-		fr.load(a, buf + kHalo + lane * kLane, pk, badacc);
+		fr.load(a, buf, pk, badacc);
 		if constexpr (kPacked) { // the tile now lives in registers (+ pk): refill the slot while we walk
 			__syncwarp();
 			refill(slot);

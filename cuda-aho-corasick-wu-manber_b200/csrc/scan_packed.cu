@@ -32,12 +32,22 @@ __device__ __forceinline__ uint32_t pack16(const uint4 r, uint32_t &badacc) {
 
 // W[0] = the 16 symbols in front of the chunk, W[1..7] = the chunk; optionally mirrored
 // into the warp's 2-bit copy pk (pk[0] = history of the tile, pk[1 + q] = tile symbols 16q..16q+15).
+// `buf` = the warp's slot: raw [64 B history][3584 B tile], or -- text packed by the host (packed_in) --
+// [16 B history][896 B tile] in the very layout of W / pk (nothing to pack: 8 LDS.32 per lane).
 template <bool STORE>
-__device__ __forceinline__ void load_pack(const uint8_t *chunk, uint32_t (&W)[8], uint32_t *pk, uint32_t &badacc) {
-	const uint4 *c4 = reinterpret_cast<const uint4 *>(chunk);
+__device__ __forceinline__ void load_pack(const ScanArgs &a, const uint8_t *buf, uint32_t (&W)[8], uint32_t *pk,
+		uint32_t &badacc) {
+	if (a.packed_in) {
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(buf) + 3 + 7 * lane_id(); // word stride 7: conflict-free
 #pragma unroll
-	for (int k = 0; k < 8; k++)
-		W[k] = pack16(c4[k - 1], badacc);
+		for (int k = 0; k < 8; k++)
+			W[k] = w[k];
+	} else {
+		const uint4 *c4 = reinterpret_cast<const uint4 *>(buf + kHalo + lane_id() * kLane);
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			W[k] = pack16(c4[k - 1], badacc);
+	}
 	if (STORE) {
 		const uint32_t lane = lane_id();
 		if (lane == 0)
@@ -110,14 +120,21 @@ struct FrontAC : PackedKey {
 		return ent & kHitMask;
 	}
 
-	__device__ __forceinline__ void load(const ScanArgs &, const uint8_t *chunk, uint32_t *pk, uint32_t &badacc) {
-		load_pack<!EXACT>(chunk, W, pk, badacc);
+	__device__ __forceinline__ void load(const ScanArgs &a, const uint8_t *buf, uint32_t *pk, uint32_t &badacc) {
+		load_pack<!EXACT>(a, buf, W, pk, badacc);
 		if (hist > 16) {
-			const uint4 *c4 = reinterpret_cast<const uint4 *>(chunk);
-			uint32_t dummy = 0;
-			H[0] = pack16(c4[-4], dummy);
-			H[1] = pack16(c4[-3], dummy);
-			H[2] = pack16(c4[-2], dummy);
+			if (a.packed_in) {
+				const uint32_t *w = reinterpret_cast<const uint32_t *>(buf) + 7 * lane_id();
+				H[0] = w[0];
+				H[1] = w[1];
+				H[2] = w[2];
+			} else {
+				const uint4 *c4 = reinterpret_cast<const uint4 *>(buf + kHalo + lane_id() * kLane);
+				uint32_t dummy = 0;
+				H[0] = pack16(c4[-4], dummy);
+				H[1] = pack16(c4[-3], dummy);
+				H[2] = pack16(c4[-2], dummy);
+			}
 		}
 	}
 
@@ -221,8 +238,8 @@ struct FrontWM : PackedKey {
 		return S > 8 ? (uint32_t) reinterpret_cast<const uint16_t *>(rmk)[ri] : (uint32_t) rmk[ri];
 	}
 
-	__device__ __forceinline__ void load(const ScanArgs &, const uint8_t *chunk, uint32_t *pk, uint32_t &badacc) {
-		load_pack<true>(chunk, W, pk, badacc);
+	__device__ __forceinline__ void load(const ScanArgs &a, const uint8_t *buf, uint32_t *pk, uint32_t &badacc) {
+		load_pack<true>(a, buf, W, pk, badacc);
 	}
 
 	__device__ __forceinline__ void walk(const ScanArgs &) {

@@ -135,9 +135,18 @@ int acwm_result_device_ptrs(acwm_matcher *mt, uint64_t **d_count, uint64_t **d_p
 int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t *count, uint64_t *positions,
 		uint64_t cap, uint64_t *n_written);
 
+/* The host-side packer acwm_search_host puts in front of the H2D copy when the matcher was built for alphabet <= 4
+ * and the text has >= 4 Mi symbols (a quarter of the bytes crosses PCIe; the scan kernel takes the packed tiles as
+ * they are): packed[i] = text[4i] | text[4i+1] << 2 | text[4i+2] << 4 | text[4i+3] << 6 for ceil(n/4) bytes, on all
+ * host cores; *bad_text = 1 if a byte >= 4 was met.  Exported for tests and for callers that keep packed corpora.
+ * Environment: ACWM_HOST_PACK=0 makes acwm_search_host copy the text one byte per symbol instead. */
+int acwm_pack_text_2bit(const uint8_t *text, uint64_t n, uint8_t *packed, int *bad_text);
+
 /* Seconds of GPU time (CUDA events around the kernels only, as the reference times
  * its kernels: cuda/cuda_wm.cu:264-289) of the last acwm_search_host call. */
 double acwm_last_kernel_seconds(const acwm_matcher *mt);
+/* Bytes of text the last acwm_search_host call copied host -> device (n, or n/4 when the host packer ran). */
+uint64_t acwm_last_h2d_bytes(const acwm_matcher *mt);
 
 /* Back-to-back scans of device-resident text: with overlap on, acwm_scan_device launches its
  * kernel as a programmatic dependent launch (griddepcontrol): CTAs of the next scan take over

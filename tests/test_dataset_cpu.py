@@ -74,3 +74,22 @@ def test_select_data_file_follows_the_reference_table():
     for bad in ((8, 3999744, 4), (8, 4628736, 20), (8, 100, 4), (8, 12345, 4)):  # the reference's fail() cases
         with pytest.raises(acwm.AcwmError):
             acwm.select_data_file(*bad)
+
+
+def test_host_packer_matches_numpy():
+    """acwm_pack_text_2bit (what acwm_search_host runs in front of the H2D copy of DNA texts) against numpy, on sizes
+    around every boundary of its loops (8 / 32 symbols, 256 Ki-symbol work items), repeated: the pool is reused."""
+    rng = np.random.default_rng(17)
+    for n in (0, 1, 3, 4, 7, 8, 31, 32, 33, 1000, 262144, 262145, 3 * 262144 + 5, (5 << 20) + 3):
+        for rep in range(2):
+            t = rng.integers(0, 4, n, dtype=np.uint8)
+            packed, bad = acwm.pack_text_2bit(t)
+            pad = np.zeros((-n) % 4, np.uint8)
+            q = np.concatenate([t, pad]).reshape(-1, 4).astype(np.uint32)
+            want = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+            assert not bad and np.array_equal(packed, want), n
+    t = rng.integers(0, 4, 700_000, dtype=np.uint8)
+    for where in (0, 5, 262143, 699_999):
+        u = t.copy()
+        u[where] = 4
+        assert acwm.pack_text_2bit(u)[1], where

@@ -171,6 +171,53 @@ def test_dense_matches_back_to_back(acwm, oracle, torch_cuda, threads, algo_name
         mt.close()
 
 
+def test_host_text_packed_on_the_host(acwm, oracle, torch_cuda):
+    """Host texts of 2-bit matchers (>= 4 Mi symbols) are packed 4 symbols per byte by the host cores before the H2D
+    copy and scanned packed: same count and positions as the oracle, for sizes that end inside a byte / a 16-byte
+    piece / a tile, for fronts with and without verification (incl. the packed-text compare for m > 16)."""
+    import os
+    dg = __import__("acwm_pkg").submodule("datagen")
+    base = dg.text_host((17 << 20) + 1000, 4, 41)
+    monkey = os.environ.get("ACWM_HOST_PACK")
+    os.environ["ACWM_HOST_PACK"] = "2"  # also on a box with few cores
+    try:
+        _host_packed_cases(acwm, oracle, dg, base)
+    finally:
+        if monkey is None:
+            os.environ.pop("ACWM_HOST_PACK", None)
+        else:
+            os.environ["ACWM_HOST_PACK"] = monkey
+
+
+def _host_packed_cases(acwm, oracle, dg, base):
+    cases = [(acwm.AC, 100, 8, {}), (acwm.WM, 1000, 16, {}), (acwm.AC, 1000, 16, {}), (acwm.WM, 20000, 32, {}),
+             (acwm.AC, 3, 70, {}), (acwm.WM, 300, (8, 64), {})]
+    for algo, p, m, opts in cases:
+        if isinstance(m, tuple):
+            pats = dg.mixed_patterns_with_hits(base, p, m[0], m[1], 4, 7)
+        else:
+            pats = dg.patterns_with_hits(base, p, m, 4, 7)
+        mt = acwm.Matcher(algo, pats, 4, **opts)
+        sizes = ((4 << 20), (4 << 20) + 1, (5 << 20) + 63, (16 << 20) + 3584 * 3 + 17, base.size)
+        if p == 1000 and algo == acwm.WM:  # once: more chunks than the pinned ring has slots
+            big = np.concatenate([base] * 15)[: (250 << 20) + 5]
+            ref = oracle.set_search(pats, big)
+            count, pos = mt.search_host(big, cap=max(1, ref["count"]))
+            assert count == ref["count"] and np.array_equal(pos, ref["positions"])
+        for n in sizes:
+            text = base[:n]
+            ref = oracle.set_search(pats, text)
+            count, pos = mt.search_host(text, cap=max(1, ref["count"]))
+            assert count == ref["count"], (algo, p, m, n)
+            assert np.array_equal(pos, ref["positions"]), (algo, p, m, n)
+        bad = base[:5 << 20].copy()
+        bad[(3 << 20) + 5] = 7
+        with pytest.raises(acwm.AcwmError) as ei:
+            mt.search_host(bad, cap=10)
+        assert ei.value.code == acwm.ERR_BAD_TEXT
+        mt.close()
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_sharded_scans_sum_to_whole(acwm, oracle, torch_cuda, world):
     """The multi-GPU geometry run on one GPU: shard scans are exactly-once."""
