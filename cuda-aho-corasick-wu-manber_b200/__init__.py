@@ -219,8 +219,10 @@ class Matcher:
         return c.value, p.value
 
     # ---- host text, end to end
-    def search_host(self, text, cap: int | None = None, want_positions: bool = True, allow_overflow: bool = False):
-        """text: numpy uint8 array (or anything exposing a host pointer via ``data_ptr``/``ctypes``)."""
+    def search_host(self, text, cap: int | None = None, want_positions: bool = True, allow_overflow: bool = False,
+                    out: np.ndarray | None = None):
+        """text: numpy uint8 array (or anything exposing a host pointer via ``data_ptr``/``ctypes``).
+        out: optional uint64 array the positions are written to (its size is the capacity)."""
         if hasattr(text, "data_ptr"):  # pinned torch tensor
             ptr, n = text.data_ptr(), text.numel()
         else:
@@ -228,8 +230,12 @@ class Matcher:
             ptr, n = text.ctypes.data, text.size
         count, nw = C.c_uint64(), C.c_uint64()
         if want_positions:
-            cap = int(cap if cap is not None else max(1, n))
-            pos = np.empty(cap, np.uint64)
+            if out is not None:
+                assert out.dtype == np.uint64 and out.flags.c_contiguous
+                pos, cap = out, int(out.size)
+            else:
+                cap = int(cap if cap is not None else max(1, n))
+                pos = np.empty(cap, np.uint64)
             pptr = pos.ctypes.data_as(C.c_void_p)
         else:
             cap, pos, pptr = 0, np.zeros(0, np.uint64), None
