@@ -212,6 +212,8 @@ def run_ours(args):
             own = np.concatenate([own, nxt])
         return own
 
+    # texts much larger than L2 (126 MB) need no rotation: every step streams from HBM anyway
+    N_ROTATE = globals()["N_ROTATE"] if n <= (256 << 20) else 1
     host_texts = [text0 if (rank == 0 and world == 1) else shard_text(TEXT_SEED, 0)]
     for k in range(1, N_ROTATE):
         host_texts.append(shard_text(TEXT_SEED, k))
@@ -304,6 +306,8 @@ def run_ours(args):
 
     # ---- end to end through the public API: pinned host text -> count + positions on the host
     pinned = [torch.from_numpy(t).pin_memory() for t in host_texts[:2]]
+    if len(pinned) == 1:
+        pinned = pinned * 2
     e2e_steps = max(3, min(args.steps, 10))
     pos_out = np.empty(pos_cap, np.uint64)  # the caller's position buffer, reused
     for i in range(2):
@@ -344,7 +348,8 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {desc}", "algo": algo_name, "alphabet": alphabet,
                        "patterns": p, "m": list(m) if isinstance(m, tuple) else m,
                        "text_bytes_per_gpu": n, "halo_bytes": halo,
-                       "l2": f"{N_ROTATE} distinct {args.text_mib} MiB texts cycled (working set > L2)",
+                       "l2": (f"{N_ROTATE} distinct {args.text_mib} MiB texts cycled (working set > L2)" if N_ROTATE > 1
+                              else f"one {args.text_mib} MiB text per GPU (larger than L2)"),
                        "positions": "count + sorted uint64 positions produced every step",
                        "count_exchange": ("none (1 GPU)" if world == 1 else
                                           "in-kernel st.release.sys into NVLink peer mailboxes (torch symmetric memory)"
