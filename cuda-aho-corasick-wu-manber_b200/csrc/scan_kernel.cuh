@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	const uint64_t cta_lo = min(a.tile_lo + (uint64_t) blockIdx.x * a.tiles_per_cta, a.tile_hi);
 	const uint64_t cta_hi = min(cta_lo + a.tiles_per_cta, a.tile_hi);
 	const uint32_t n_b = (uint32_t) (cta_hi - cta_lo);
-	const uint64_t stream_pol = policy_evict_first();
 	const uint32_t tab_bytes = front_smem + rm_bytes + f2_bytes;
 
 	// ---- prologue: every warp arms its own barriers and starts its first tile(s) at once (static claims
@@ -147,6 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 				// the generic-proxy reads of this slot are done (__syncwarp before us): order
 				// them before the async-proxy write
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				const uint64_t stream_pol = policy_evict_first(); // made where it is used: not two registers held across the scan
 				if (kPacked && a.packed_in) {
 					mbar_expect_tx(&bars[s], kLoadBytes / 4);
 					tma_bulk_g2s(dst, a.text16 + t * (uint64_t) (kTile / 4) - kHalo / 4, kLoadBytes / 4, &bars[s], stream_pol);
@@ -210,7 +210,6 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		trace_mark(a, 9);
 		trace_mark(a, 10); // 2 -> 9 -> 10: what a stamp itself costs
 	}
-	uint32_t n_scanned = 0;
 
 	uint32_t badacc = 0;
 	Work *wk = &a.ctl->work[a.epoch % 3u];
@@ -256,7 +255,6 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 				trace_mark(a, 3);
 		}
 		fr.walk(a);
-		n_scanned++;
 
 		em.tile = tile;
 		em.idx = idx;
@@ -437,10 +435,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 		if constexpr (!kPacked)
 			refill(slot);
 	}
-	if (a.trace && lane == 0) {
+	if (a.trace && lane == 0)
 		trace_mark(a, 48 + warp);
-		a.trace[(size_t) blockIdx.x * kTraceWords + 80 + warp] = n_scanned;
-	}
 	if (!tab_ready)
 		mbar_wait(tab_bar, 0); // a warp without a tile: the CTA must not retire under its own table copy
 	em.finish();

@@ -2,7 +2,7 @@
  * main.c uses ac/ac.c, wu/wu.c and cuda/cuda_{ac,wm}.cu: same entry points, same
  * caller-side allocation and initialisation of the flat tables, same report lines.
  *
- *   smatcher_main <ac|wm> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-seed S]
+ *   smatcher_main <ac|wm> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-data DIR [-c]] [-seed S]
  *
  * It is the integration example of INTEGRATION.md (what a maintainer of the reference
  * links instead of the reference's own objects) and the small CLI equivalent of
@@ -10,7 +10,12 @@
  * has commented out (main.c:519-531), the text/pattern files replace the missing
  * load_files helper (main.c:453) and, without files, a seeded generator plays the role
  * of create_multiple_pattern_with_hits (main.c:49): half of the patterns are windows
- * of the text.  Text and pattern bytes are symbol codes in [0, alphabet).
+ * of the text.  Text and pattern bytes are symbol codes in [0, alphabet); a -text file that
+ * holds a raw corpus (FASTA nucleotides / amino acids, English text) is mapped to codes by
+ * the library's loader (acwm_load_text).  With -data DIR the corpus and the pattern file
+ * are chosen the way the reference's select_data_file does (main.c:31-123: the text size
+ * -n selects the corpus under DIR/text, patterns in DIR/pattern/<n>/<m>/<alphabet>/pattern);
+ * -c draws the pattern set "with hits" from the text instead of reading it (main.c:49).
  *
  * Build:  gcc -O2 -I include examples/smatcher_main.c -L cuda-aho-corasick-wu-manber_b200 \
  *             -lacwm_b200 -Wl,-rpath,'$ORIGIN/../cuda-aho-corasick-wu-manber_b200' -o examples/smatcher_main
@@ -23,7 +28,7 @@
 #include "acwm.h" /* declares the smatcher.h entry points + cuda_acN / cuda_wmN */
 
 static void usage(void) {
-	fprintf(stderr, "usage: smatcher_main <ac|wm> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-seed S]\n");
+	fprintf(stderr, "usage: smatcher_main <ac|wm> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-data DIR [-c]] [-seed S]\n");
 	exit(2);
 }
 
@@ -52,7 +57,10 @@ static double now_s(void) {
 
 int main(int argc, char **argv) {
 	int m = 0, n = 0, p_size = 0, alphabet = 0, B = 3, i, j;
-	const char *text_file = NULL, *pattern_file = NULL;
+	const char *text_file = NULL, *pattern_file = NULL, *data_root = NULL;
+	int create_data = 0;
+	unsigned long long seed = 0;
+	static char sel_text[4096], sel_pattern[4096];
 	if (argc < 2 || (strcmp(argv[1], "ac") && strcmp(argv[1], "wm")))
 		usage();
 	const int use_ac = strcmp(argv[1], "ac") == 0;
@@ -63,10 +71,26 @@ int main(int argc, char **argv) {
 		if (!strcmp(argv[i], "-alphabet")) alphabet = atoi(argv[i + 1]);
 		if (!strcmp(argv[i], "-text")) text_file = argv[i + 1];
 		if (!strcmp(argv[i], "-pattern")) pattern_file = argv[i + 1];
-		if (!strcmp(argv[i], "-seed")) rng_state ^= (unsigned long long) atoll(argv[i + 1]) * 0x9E3779B97F4A7C15ull;
+		if (!strcmp(argv[i], "-data")) data_root = argv[i + 1];
+		if (!strcmp(argv[i], "-seed")) {
+			seed = (unsigned long long) atoll(argv[i + 1]);
+			rng_state ^= seed * 0x9E3779B97F4A7C15ull;
+		}
 	}
+	for (i = 2; i < argc; i++)
+		if (!strcmp(argv[i], "-c"))
+			create_data = 1; /* main.c:362: regenerate the pattern set with hits */
 	if (m <= 0 || n <= 0 || p_size <= 0 || alphabet <= 0)
 		usage();
+	if (data_root) { /* select_data_file, main.c:31-123 */
+		if (acwm_select_data_file((uint32_t) m, (uint64_t) n, (uint32_t) alphabet, data_root, sel_pattern, sel_text,
+					sizeof(sel_text)) != ACWM_OK) {
+			fprintf(stderr, "%s\n", acwm_last_error());
+			return 1;
+		}
+		text_file = sel_text;
+		pattern_file = create_data ? NULL : sel_pattern;
+	}
 
 	/* ---- inputs: text[n], pattern[p_size][m] (+1 byte: the reference reads one past, ac/ac.c:136) and the flat copy */
 	unsigned char *text = (unsigned char *) malloc((size_t) n);
@@ -74,13 +98,22 @@ int main(int argc, char **argv) {
 	unsigned char *pattern2 = (unsigned char *) malloc((size_t) m * p_size);
 	if (!text || !pattern || !pattern2)
 		return 1;
-	if (text_file)
-		read_exact(text_file, text, (size_t) n);
-	else
+	if (text_file) { /* load_files, main.c:453: the first n symbols of the corpus, as codes */
+		uint8_t *loaded = NULL;
+		uint64_t got = 0;
+		if (acwm_load_text(text_file, (uint32_t) alphabet, (uint64_t) n, &loaded, &got) != ACWM_OK || got < (uint64_t) n) {
+			fprintf(stderr, "cannot load %d symbols from %s: %s\n", n, text_file, loaded ? "corpus too short" : acwm_last_error());
+			return 1;
+		}
+		memcpy(text, loaded, (size_t) n);
+		acwm_free_text(loaded);
+	} else
 		for (i = 0; i < n; i++)
 			text[i] = (unsigned char) (rng_next() % (unsigned) alphabet);
 	if (pattern_file)
 		read_exact(pattern_file, pattern2, (size_t) m * p_size);
+	else if (data_root) /* create_multiple_pattern_with_hits, main.c:49 */
+		acwm_patterns_with_hits(text, (uint64_t) n, (uint32_t) m, (uint32_t) p_size, (uint32_t) alphabet, seed, 50, pattern2);
 	else
 		for (j = 0; j < p_size; j++) {
 			if (j % 2 == 0 && n >= m) { /* "with hits" */

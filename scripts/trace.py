@@ -66,13 +66,6 @@ for a_, b_ in ((0, 1), (1, 2), (2, 3), (0, 3), (3, 4), (4, 5), (5, 6), (6, 7), (
 log(f"  cost of one stamp (two back-to-back pairs): {np.median(T[2:, :, 9] - T[2:, :, 2])/1e3:.2f} {np.median(T[2:, :, 10] - T[2:, :, 9])/1e3:.2f}")
 first = (T[2:, :, 16:48] - T[2:, :, 0:1]) / 1e3
 end = (T[2:, :, 48:80] - T[2:, :, 0:1]) / 1e3
-tiles = T[2:, :, 80:112]
-log(f"  first tile in registers after entry: med {np.median(first):6.2f} p90 {np.percentile(first,90):6.2f} max {first.max():6.2f}")
-log(f"  warp scan-loop end after entry:      med {np.median(end):6.2f} min {end.min():6.2f} max {end.max():6.2f}")
-log(f"  within-CTA spread of warp ends (max-min): med {np.median(end.max(2)-end.min(2)):6.2f}  mean idle per warp before the CTA sync {np.mean(end.max(2,keepdims=True)-end):6.2f}")
-log(f"  tiles per warp: min {tiles.min():.0f} med {np.median(tiles):.0f} max {tiles.max():.0f}")
-per_tile = (end - first) / np.maximum(tiles, 1)
-log(f"  us per tile per warp (scan loop / tiles): med {np.median(per_tile):6.3f}")
 cta_scan_end = T[2:, :, 4] - T[2:, :, 0]
 log(f"  CTA scan time (entry -> all warps done): med {np.median(cta_scan_end)/1e3:6.2f} min {cta_scan_end.min()/1e3:6.2f} max {cta_scan_end.max()/1e3:6.2f}")
 gap = (T[3:, :, 0].min(1) - T[2:-1, :, 8].max(1)) / 1e3

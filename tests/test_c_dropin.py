@@ -47,3 +47,28 @@ def test_c_driver_prints_oracle_counts(acwm, oracle, tmp_path, idx):
     assert int(re.search(first + r" \t(\d+)\t", out).group(1)) == want
     assert int(re.search(r"Kernel 5 matches \t(\d+)\t", out).group(1)) == want
     assert int(re.search(r"Total results: (\d+)\.", out).group(1)) == want
+
+
+@pytest.mark.gpu
+def test_c_driver_selects_and_loads_a_corpus(acwm, oracle, tmp_path):
+    """-data DIR -c: the corpus is chosen like the reference's select_data_file (n = 4628736 -> text/E.coli2), loaded
+    from FASTA through the library's symbol map, the pattern set drawn with hits -- and the printed counts are the
+    oracle's on the same symbols and patterns."""
+    _build(acwm)
+    n, m, p = 4628736, 8, 100
+    rng = np.random.default_rng(12)
+    seq = rng.integers(0, 4, n + 1000, dtype=np.uint8)
+    letters = np.frombuffer(b"ACGT", np.uint8)[seq]
+    (tmp_path / "text").mkdir()
+    with open(tmp_path / "text" / "E.coli2", "wb") as f:
+        f.write(b">synthetic E. coli\n")
+        for i in range(0, letters.size, 70):
+            f.write(letters[i:i + 70].tobytes() + b"\n")
+    out = subprocess.run([EXE, "wm", "-m", str(m), "-n", str(n), "-p_size", str(p), "-alphabet", "4", "-data", str(tmp_path),
+                          "-c", "-seed", "5"], capture_output=True, text=True, check=True, timeout=300).stdout
+    text = acwm.load_text(str(tmp_path / "text" / "E.coli2"), 4, n)
+    assert np.array_equal(text, seq[:n])
+    pats = acwm.patterns_with_hits(text, m, p, 4, seed=5, hit_percent=50)
+    want = oracle.set_search(pats, text)["count"]
+    assert int(re.search(r"search_wm2 matches \t(\d+)\t", out).group(1)) == want
+    assert int(re.search(r"Total results: (\d+)\.", out).group(1)) == want
