@@ -20,7 +20,7 @@ constexpr uint32_t kPackWords = 1 + kTile / 16 + 3; // 2-bit copy of the tile (+
 constexpr uint32_t kMaxStages = 4;
 constexpr uint32_t kMaxPeers = 16;                  // ranks of the in-kernel count exchange
 constexpr uint32_t kPeerRing = 4;                   // mailbox slots per rank pair: epochs in flight
-constexpr uint32_t kListCap = 64;                   // per-warp list of match positions of one tile (cooperative stores)
+constexpr uint32_t kListCap = 128;                  // per-warp list of match positions of one tile (cooperative stores)
 constexpr uint32_t kLogCap = 24;                    // per-warp log of its staging reservations (they double in size)
 constexpr uint32_t kMaxGrabLog2 = 23;               // largest single reservation: 2^23 slots
 
