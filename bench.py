@@ -369,7 +369,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "scan_kernel (one cooperative launch: TMA-fed scan + position ordering)",
+                         "kernel": "scan_kernel (one launch: TMA-fed scan + barrier-free position ordering)",
                          "kernel_ms": scan_mean * 1e3, "kernel_ms_isolated_launch": scan_isolated * 1e3,
                          "duration_source": "timed region / K (one launch per step)" if scan_mean != scan_isolated
                          else "CUDA events around single launches",

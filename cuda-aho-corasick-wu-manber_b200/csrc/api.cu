@@ -124,6 +124,8 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	CU(cudaMallocHost((void **) &mt->h_res, sizeof(Result)));
 	CU(cudaMallocHost((void **) &mt->h_bounce, kBounceEntries * 8));
 	CU(cudaMalloc((void **) &mt->d_cta_total, 2 * kMaxScanBlocks * sizeof(unsigned long long)));
+	// the span totals are recognised by their launch tag: recycled device memory must not hold a look-alike
+	CU(cudaMemset(mt->d_cta_total, 0, 2 * kMaxScanBlocks * sizeof(unsigned long long)));
 	CU(cudaStreamCreateWithFlags(&mt->s_copy, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&mt->s_scan, cudaStreamNonBlocking));
 	for (auto &e : mt->ev_copy)
@@ -167,7 +169,7 @@ static uint32_t kernel_tune() {
 }
 
 // Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
-// cooperative kernel that scans, orders the positions and publishes the result block.
+// kernel that scans, orders the positions and publishes the result block.
 static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
 		uint64_t tile_hi, int want_positions, int append, int exchange, cudaStream_t st, int packed_in = 0) {
 	const Compiled &c = mt->c;

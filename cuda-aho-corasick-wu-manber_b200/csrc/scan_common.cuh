@@ -39,7 +39,7 @@ constexpr unsigned kMailShift = 48;   // mailbox word of the count exchange: [ep
 // Per-CTA totals carry the launch number, so a stale value is never mistaken for this launch's: [tag : 24 | matches : 40]
 constexpr unsigned kTotalShift = 40;
 constexpr unsigned long long kTotalMask = (1ull << kTotalShift) - 1;
-constexpr unsigned long long kLookbackTimeoutNs = 200ull * 1000 * 1000; // a predecessor that never shows up: report, do not hang
+constexpr unsigned long long kLookbackTimeoutNs = 2000ull * 1000 * 1000; // a predecessor that never shows up: report, do not hang
 // Work.bad_text bits: 1 = text byte >= 4 on the 2-bit path, 4 = a warp's reservation log overflowed (reported as overflow)
 // ScanArgs.tune bits
 constexpr uint32_t kTuneCoopVerify = 1u;
@@ -174,7 +174,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 			: "memory");
 }
 
-// ------------------------------------------------------------ grid-wide arrival (cooperative launch: all CTAs resident)
+// ------------------------------------------------------------ arrival / look-back loads
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
 	unsigned long long v;
 	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

@@ -1,23 +1,25 @@
 // The scan kernel skeleton (sm_100a), shared by every front end.
 //
-// ONE cooperative launch does the whole job -- supersedes the reference's
-// kernel + D2H of 7680 per-thread counters + host sum (cuda/cuda_ac.cu:654-673):
+// ONE launch does the whole job -- supersedes the reference's kernel + D2H of 7680 per-thread
+// counters + host sum (cuda/cuda_ac.cu:654-673) -- and no CTA ever waits for the whole grid:
 //
 //   1. scan     one persistent CTA per SM owns a contiguous span of warp tiles; every warp
 //               runs its own TMA pipeline over the span (cp.async.bulk global -> shared,
-//               mbarrier complete_tx, 2-3 tiles in flight per warp, no block-wide barrier),
-//               walks its front end over the raw tile and stages each match as
-//               [tile | rank-in-tile | pos-in-tile] through one warp-aggregated atomic;
-//   2. order    the CTA turns the per-tile counts of its span into exclusive offsets, all
-//               CTAs meet at one grid barrier, every CTA derives the span bases from the
-//               per-CTA totals and the staged matches drop into their sorted slots;
-//   3. publish  the arrival at the grid barrier is ONE 64-bit atomic per CTA that also carries
-//               the CTA's match count; the last CTA to arrive writes the result block.  The
-//               working counters are double-buffered by launch parity, each launch clears its
-//               successor's copy (no memset node between scans).
-// Overlap mode (acwm_set_overlap): the launch is a programmatic dependent launch -- its prologue and its
-// read-only scan phase start while the previous scan of the stream retires (griddepcontrol), and wait
-// for that scan to complete right before their first write to the scratch arrays.
+//               mbarrier complete_tx, no block-wide barrier), walks its front end over the tile,
+//               checks the candidates (warp-cooperatively when they are few) and stages each match as
+//               [tile | rank-in-tile | pos-in-tile] in blocks it reserves from the launch's cursor
+//               (doubling sizes, logged per warp in shared memory);
+//   2. order    the CTA turns the per-tile counts of its span into exclusive offsets (shared memory),
+//               publishes the span total as a tagged word and looks back over the totals of the spans
+//               in front of it; then every warp moves its own staged matches to their sorted slots;
+//   3. publish  a CTA's arrival is ONE 64-bit atomic that also carries its match count; the last
+//               CTA to arrive writes the result block.  The working counters exist three times
+//               (launch k uses copy k % 3 and zeroes copy k + 1 as it starts), the scratch arrays twice
+//               (by launch parity): no memset node between scans.
+// Overlap mode (acwm_set_overlap): the launch is a programmatic dependent launch -- CTAs of scan k + 1 take
+// over SMs as CTAs of scan k retire and run their whole scan phase on their own copies of the scratch state;
+// thread 0 waits for scan k (griddepcontrol.wait) only before the arrival.  At most two scans are in flight
+// (see Work in scan_common.cuh).
 //   4. exchange (multi-GPU) the publishing thread stores the rank's count into every peer's mailbox
 //               over NVLink (system-scope stores on peer-mapped memory) and, at its very end, sums
 //               what the peers left in its own mailbox for the PREVIOUS scan: an all-reduce of the
@@ -653,10 +655,10 @@ static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid,
 	cfg.blockDim = dim3(THREADS);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = st;
-	// The grid barrier needs every CTA resident: grid <= #SMs at one CTA per SM, and the launch is cooperative
-	// so that the runtime checks it.  Overlap mode trades that check for a programmatic dependent launch (the
-	// two attributes together serialise, profiles/README.md session i): the grid is the same, so the CTAs
-	// still all become resident as the previous scan's CTAs retire.
+	// One CTA per SM (grid <= #SMs).  Plain scans are launched cooperatively (the runtime checks that the grid
+	// is resident at once: the span look-back then never waits for a CTA that has not started); overlap mode
+	// trades that for a programmatic dependent launch -- used only for grids of SM-filling CTAs, which all find
+	// an SM as the previous scan's CTAs retire (the two attributes together serialise, profiles/README.md session i).
 	cudaLaunchAttribute attr[1];
 	if (a.pdl) {
 		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -332,6 +332,79 @@ def test_baseline_configs_full_size(acwm, oracle, have_ref, torch_cuda):
         other.close()
 
 
+def _planted(torch, d_text, pats, ends):
+    """Overwrite d_text so that pattern k ends at ends[k]; returns the sorted ends."""
+    for k, e in enumerate(ends):
+        q = np.ascontiguousarray(pats[k])
+        d_text[e - q.size + 1:e + 1] = torch.from_numpy(q).cuda()
+    return np.array(sorted(ends), np.uint64)
+
+
+def test_baseline_configs_3_and_4_full_size_by_planting(acwm, torch_cuda):
+    """BASELINE configs[2] (one GPU's shard: 1e9 bytes of DNA, 100 000 patterns of 32) and configs[3] (2e9 bytes over 256
+    symbols, 10 000 patterns of 8..64 bytes) at their real sizes.  On texts this random no pattern occurs by chance
+    (1e9 * 1e5 / 4^32 ~ 5e-6; 2e9 * 1e4 / 256^8 ~ 1e-9), so the result must be EXACTLY the planted occurrences: count,
+    every position, ascending.  Plus: AC == WM on the same set, a second scan gives the same result, and two shards
+    with an (m_max-1)-byte halo report every match exactly once (main.c:467-477)."""
+    torch = torch_cuda
+    dg = __import__("acwm_pkg").submodule("datagen")
+    sh = __import__("acwm_pkg").submodule("sharding")
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(21)
+    T = 3584  # warp tile: plant around its edges too
+
+    # ---- configs[2]: equal-length DNA patterns, AC (automaton in L2) and WM
+    n = 1_000_000_000
+    d_text = dg.text_device(n, 4, 11)
+    pats = rng.integers(0, 4, (100_000, 32), dtype=np.uint8)
+    # windows must not overlap (a later plant would overwrite an earlier one): >= 32 apart
+    fixed = [31, T - 1, T + 31, 5 * T + 17, n // 2 - 1, n // 2 + 40, n - 1 - 64, n - 1]
+    rnd = [int(x) for x in rng.integers(10_000, n - 10_000, 40) // 100 * 100 + 99]
+    ends = sorted(set(fixed + [e for e in rnd if all(abs(e - f) > 200 for f in fixed)]))
+    want = _planted(torch, d_text, pats[:len(ends)], ends)
+    results = []
+    for algo in (acwm.AC, acwm.WM):
+        mt = acwm.Matcher(algo, pats, 4).upload(pos_capacity=1 << 20)
+        for rep in range(2):
+            mt.scan_tensor(d_text)
+            count, pos, _ = mt.fetch(cap=1 << 20, stream=st)
+            assert count == want.size and np.array_equal(pos, want), (algo, rep)
+        got = []
+        for r in range(2):
+            start, length, report_from = sh.shard_of(n, 2, r, 32)
+            mt.scan_tensor(d_text[start:start + length], report_from=report_from)
+            c, ppos, _ = mt.fetch(cap=1 << 20, stream=st)
+            got.append(ppos + np.uint64(start))
+        assert np.array_equal(np.concatenate(got), want), algo
+        results.append(pos)
+        mt.close()
+    assert np.array_equal(results[0], results[1])
+    del d_text
+
+    # ---- configs[3]: mixed-length byte patterns (WM; the reference has no mixed-length mode: union over lengths)
+    n = 2_000_000_000
+    d_text = dg.text_device(n, 256, 12)
+    lens = rng.integers(8, 65, 10_000)
+    mixed = [rng.integers(0, 256, int(L), dtype=np.uint8) for L in lens]
+    fixed = [63, T - 1, T + 70, n // 2 + 5, n - 1]
+    rnd = [int(x) for x in rng.integers(10_000, n - 10_000, 55) // 200 * 200 + 150]
+    ends = sorted(set(fixed + [e for e in rnd if all(abs(e - f) > 200 for f in fixed)]))
+    want = _planted(torch, d_text, mixed[:len(ends)], ends)
+    mt = acwm.Matcher(acwm.WM, mixed, 256).upload(pos_capacity=1 << 20)
+    for rep in range(2):
+        mt.scan_tensor(d_text)
+        count, pos, _ = mt.fetch(cap=1 << 20, stream=st)
+        assert count == want.size and np.array_equal(pos, want), rep
+    got = []
+    for r in range(2):
+        start, length, report_from = sh.shard_of(n, 2, r, 64)
+        mt.scan_tensor(d_text[start:start + length], report_from=report_from)
+        c, ppos, _ = mt.fetch(cap=1 << 20, stream=st)
+        got.append(ppos + np.uint64(start))
+    assert np.array_equal(np.concatenate(got), want)
+    mt.close()
+
+
 def test_multi_gib_text_positions_beyond_32_bits(acwm, torch_cuda):
     """5 GiB DNA text resident in HBM: 64-bit positions, AC == WM, planted matches found."""
     torch = torch_cuda
