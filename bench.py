@@ -361,8 +361,9 @@ def run_ours(args):
                                                         "table_in_smem", "smem_bytes", "threads", "stages")}},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(mt.last_h2d_bytes),
                     "text_bytes_per_step": e2e_bytes,
-                    "h2d": ("text packed to 2 bits per symbol by the host cores (csrc/hostpack.cpp), a quarter of the "
-                            "bytes on the link" if mt.last_h2d_bytes < e2e_bytes else "text copied one byte per symbol"),
+                    "h2d": ("hybrid: a prefix of the text copied one byte per symbol by DMA while the host cores pack the "
+                            "rest to 2 bits per symbol (csrc/hostpack.cpp)" if mt.last_h2d_bytes < e2e_bytes
+                            else "text copied one byte per symbol"),
                     "d2h_bytes_per_step": 8 * int(e2e_count if world == 1 else last_count) + 32,
                     "steps": e2e_steps, "api": "acwm_search_host (pinned host text -> host count + positions)"},
             "gpu_launches": int(launches),

@@ -252,6 +252,12 @@ constexpr unsigned kHostPackMinThreads = 10;
 constexpr uint64_t kPackChunk = 56 * HostPacker::kPieceSymbols; // 14 Mi symbols = 4096 tiles = 56 work items
 constexpr unsigned kPackRing = 16;
 static_assert(kPackChunk % kTile == 0 && kPackChunk % 64 == 0, "chunks are whole tiles and whole 16-byte pieces");
+// ACWM_HOST_RAW_PERCENT: share of a pinned host text that is sent unpacked beside the packed rest (default 30; 0 = none)
+static unsigned host_raw_percent() {
+	const char *e = getenv("ACWM_HOST_RAW_PERCENT");
+	const long v = e && *e ? atol(e) : 30;
+	return (unsigned) std::min<long>(std::max<long>(v, 0), 90);
+}
 // ACWM_HOST_PACK: 0 = never, 2 = always (tests), unset / 1 = when the host has the cores for it
 static int host_pack_mode() {
 	const char *e = getenv("ACWM_HOST_PACK");
@@ -302,18 +308,62 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		HostPacker &p;
 		~Release() { p.finish(); }
 	} release{pk};
-	pk.begin(text, n, kPackChunk, mt->h_pack_ring, slot_bytes, kPackRing);
-	uint64_t oldest = 0; // first chunk whose copy is not known to be complete (its ring slot is still taken)
-	for (uint64_t ci = 0; ci < n_chunks; ci++) {
+	// The link moves raw text by DMA while the cores pack: a prefix of the text (whole chunks, ~30 %: about where link
+	// time and packing time meet at ~50 GB/s raw and ~93 GB/s packing) goes one byte per symbol from the caller's
+	// PINNED buffer on a second copy stream, the rest is packed.  The packed part brings its own history (the 64-symbol
+	// halo of its first tile and the reach of the longest pattern's compare), packed by this thread.
+	uint64_t R = 0;
+	const uint32_t H = (std::max<uint32_t>(64u, mt->c.prm.m_max) + 63u) & ~63u;
+	if (n_chunks >= 5 && H <= 4096 && host_raw_percent() > 0) {
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, text) == cudaSuccess && at.type == cudaMemoryTypeHost)
+			R = std::min<uint64_t>(n_chunks - 1, (n_chunks * host_raw_percent() + 50) / 100);
+		(void) cudaGetLastError();
+	}
+	const uint64_t n_raw = R * kPackChunk;
+	if (R) {
+		if (n_raw + 64 > mt->raw_cap) {
+			if (mt->d_raw)
+				cudaFree(mt->d_raw);
+			mt->d_raw = nullptr;
+			mt->raw_cap = 0;
+			CU(cudaMalloc((void **) &mt->d_raw, n_raw + 64));
+			mt->raw_cap = n_raw + 64;
+		}
+		if (!mt->s_copy2) {
+			CU(cudaStreamCreateWithFlags(&mt->s_copy2, cudaStreamNonBlocking));
+			CU(cudaMallocHost((void **) &mt->h_hist, 4096 / 4 + 16));
+		}
+	}
+	pk.begin(text + n_raw, n - n_raw, kPackChunk, mt->h_pack_ring, slot_bytes, kPackRing);
+	for (uint64_t ci = 0; ci < R; ci++) { // the raw prefix: all copies and scans queued at once
+		const uint64_t b0 = ci * kPackChunk;
+		CU(cudaMemcpyAsync(mt->d_raw + b0, text + b0, kPackChunk, cudaMemcpyHostToDevice, mt->s_copy2));
+		cudaEvent_t ev = mt->ev_copy[ci % mt->ev_copy.size()];
+		CU(cudaEventRecord(ev, mt->s_copy2));
+		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
+		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
+		if ((rc = launch_scan(mt, mt->d_raw, n_raw, 0, ci * chunk_tiles, (ci + 1) * chunk_tiles, want_positions, ci > 0, 0,
+					 mt->s_scan, 0)))
+			return rc;
+		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
+	}
+	if (R) {
+		HostPacker::pack_now(text + n_raw - H, mt->h_hist, H);
+		CU(cudaMemcpyAsync(mt->d_text + (n_raw - H) / 4, mt->h_hist, H / 4, cudaMemcpyHostToDevice, mt->s_copy));
+	}
+	uint64_t oldest = 0; // first packed chunk whose copy is not known to be complete (its ring slot is still taken)
+	for (uint64_t ci = R; ci < n_chunks; ci++) {
 		const uint64_t b0 = std::min<uint64_t>(n, ci * kPackChunk), b1 = std::min<uint64_t>(n, (ci + 1) * kPackChunk);
-		while (ci >= oldest + kPackRing) { // the packers may not start this chunk before its slot is free
+		const uint64_t cj = ci - R; // chunk number of the packing job
+		while (cj >= oldest + kPackRing) { // the packers may not start this chunk before its slot is free
 			CU(cudaEventSynchronize(mt->ev_pack[oldest % kPackRing]));
 			pk.recycle(oldest++);
 		}
 		const double t0 = now();
-		pk.wait_chunk(ci);
+		pk.wait_chunk(cj);
 		t_wait += now() - t0;
-		uint8_t *slot = mt->h_pack_ring + (ci % kPackRing) * slot_bytes;
+		uint8_t *slot = mt->h_pack_ring + (cj % kPackRing) * slot_bytes;
 		const uint64_t used = (b1 - b0 + 3) / 4, bytes = ((b1 - b0 + 63) / 64) * 16;
 		if (bytes > used)
 			memset(slot + used, 0, bytes - used); // the last piece of the text: zero padding
@@ -321,7 +371,7 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 			t_issued.push_back((now() - t_begin) * 1e3);
 		if (bytes)
 			CU(cudaMemcpyAsync(mt->d_text + b0 / 4, slot, bytes, cudaMemcpyHostToDevice, mt->s_copy));
-		cudaEvent_t ev = mt->ev_pack[ci % kPackRing];
+		cudaEvent_t ev = mt->ev_pack[cj % kPackRing];
 		CU(cudaEventRecord(ev, mt->s_copy));
 		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
 		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
@@ -329,12 +379,12 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, 0, mt->s_scan, 1)))
 			return rc;
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
-		while (oldest < ci && cudaEventQuery(mt->ev_pack[oldest % kPackRing]) == cudaSuccess)
+		while (oldest < cj && cudaEventQuery(mt->ev_pack[oldest % kPackRing]) == cudaSuccess)
 			pk.recycle(oldest++); // let the packers run further ahead
 	}
 	(void) cudaGetLastError(); // cudaEventQuery's cudaErrorNotReady is not an error
 	const uint64_t bad = pk.bad();
-	mt->last_h2d_bytes = packed_total;
+	mt->last_h2d_bytes = n_raw + (packed_total - n_raw / 4) + (R ? H / 4 : 0);
 	mt->last_want_positions = want_positions;
 	const double t_issue = now();
 	rc = acwm_fetch(mt, count, positions, cap, n_written, mt->s_scan);
@@ -359,8 +409,9 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		fprintf(stderr, "\n");
 	}
 	if (dbg)
-		fprintf(stderr, "acwm host-packed search: n %llu, %llu chunks, %u threads: waited for the packers %.3f ms, issue loop %.3f ms, fetch %.3f ms, kernels %.3f ms\n",
-				(unsigned long long) n, (unsigned long long) n_chunks, pk.threads(), t_wait * 1e3, (t_issue - t_begin) * 1e3,
+		fprintf(stderr, "acwm host-packed search: n %llu, %llu chunks (%llu of them sent unpacked), %u threads: waited for the packers %.3f ms, issue loop %.3f ms, fetch %.3f ms, kernels %.3f ms\n",
+				(unsigned long long) n, (unsigned long long) n_chunks, (unsigned long long) R, pk.threads(), t_wait * 1e3,
+				(t_issue - t_begin) * 1e3,
 				(now() - t_issue) * 1e3, secs * 1e3);
 	if (bad & 0xFCFCFCFCFCFCFCFCull)
 		return set_error(ACWM_ERR_BAD_TEXT, "text holds a byte >= 4 but the matcher was built for alphabet <= 4");
@@ -684,6 +735,12 @@ void acwm_free(acwm_matcher *mt) {
 			cudaFreeHost(mt->h_bounce);
 		if (mt->h_pack_ring)
 			cudaFreeHost(mt->h_pack_ring);
+		if (mt->h_hist)
+			cudaFreeHost(mt->h_hist);
+		if (mt->d_raw)
+			cudaFree(mt->d_raw);
+		if (mt->s_copy2)
+			cudaStreamDestroy(mt->s_copy2);
 		for (auto e : mt->ev_pack)
 			if (e)
 				cudaEventDestroy(e);

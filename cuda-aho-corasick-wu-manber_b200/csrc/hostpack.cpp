@@ -205,6 +205,8 @@ void HostPacker::recycle(uint64_t c) {
 	gate_.store(c + cur_.ring_chunks + 1, std::memory_order_release);
 }
 
+uint64_t HostPacker::pack_now(const uint8_t *src, uint8_t *dst, uint64_t n_sym) { return pick_pack()(src, dst, n_sym); }
+
 uint64_t HostPacker::pack(const uint8_t *src, uint8_t *dst, uint64_t n_sym) {
 	if (n_sym == 0)
 		return 0;

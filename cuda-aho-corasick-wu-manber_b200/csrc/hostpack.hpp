@@ -24,6 +24,9 @@ public:
 	// Returns the OR of all source bytes: a bit above the low two = a symbol >= 4 in the text.
 	uint64_t pack(const uint8_t *src, uint8_t *dst, uint64_t n_sym);
 
+	// The same on the calling thread alone (small pieces).
+	static uint64_t pack_now(const uint8_t *src, uint8_t *dst, uint64_t n_sym);
+
 	// Streaming form: the text is packed chunk by chunk (chunk_sym symbols, a multiple of kPieceSymbols) into a ring
 	// of ring_chunks slots of slot_bytes; the workers run ahead of the caller, who takes the chunks in order:
 	//   begin(); for c: wait_chunk(c) [helps packing meanwhile]; <copy slot c % ring>; recycle(c - ring + 1) once that

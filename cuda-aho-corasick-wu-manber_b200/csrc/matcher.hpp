@@ -52,6 +52,10 @@ struct acwm_matcher {
 	std::array<cudaEvent_t, 4> ev_copy{};
 	acwm::HostPacker *packer = nullptr;      // 2-bit host packer (alphabet <= 4 host texts), created on first use
 	uint8_t *h_pack_ring = nullptr;          // pinned ring the packer writes and the H2D copies read
+	uint8_t *h_hist = nullptr;               // pinned: packed history in front of the packed part of a hybrid transfer
+	uint8_t *d_raw = nullptr;                // device copy of the unpacked prefix of a hybrid transfer
+	uint64_t raw_cap = 0;
+	cudaStream_t s_copy2 = nullptr;          // its copy stream
 	std::array<cudaEvent_t, 16> ev_pack{};    // one per ring slot: its copy is done
 	std::vector<cudaEvent_t> ev_time;
 	std::array<cudaEvent_t, 2> ev_prof{};

@@ -204,6 +204,14 @@ def _host_packed_cases(acwm, oracle, dg, base):
             ref = oracle.set_search(pats, big)
             count, pos = mt.search_host(big, cap=max(1, ref["count"]))
             assert count == ref["count"] and np.array_equal(pos, ref["positions"])
+        # from PINNED memory a prefix of the text travels unpacked beside the packed rest (>= 5 chunks of 14 Mi symbols)
+        import torch
+        pinned = torch.from_numpy(np.concatenate([base] * 5)[: (75 << 20) + 1001]).pin_memory()
+        ref = oracle.set_search(pats, pinned.numpy())
+        for rep in range(2):
+            count, pos = mt.search_host(pinned, cap=max(1, ref["count"]))
+            assert count == ref["count"], (algo, p, m, "pinned", rep)
+            assert np.array_equal(pos, ref["positions"]), (algo, p, m, "pinned", rep)
         for n in sizes:
             text = base[:n]
             ref = oracle.set_search(pats, text)
