@@ -102,6 +102,9 @@ def lib():
         L.acwm_shard_bounds.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u64p]
         L.acwm_shard_bounds.restype = None
         L.acwm_table_blob.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _u64p]
+        L.acwm_device_count.restype = C.c_int
+        L.acwm_search_host_sharded.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint64, _u64p,
+                                               C.c_void_p, C.c_uint64, _u64p, _u64p]
         L.acwm_set_trace.argtypes = [C.c_void_p, C.c_void_p]
         L.acwm_pack_text_2bit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_int)]
         L.acwm_trace_words_per_cta.restype = C.c_uint32
@@ -140,6 +143,36 @@ def shard_bounds(n: int, world: int, rank: int, halo: int):
     s, l = C.c_uint64(), C.c_uint64()
     lib().acwm_shard_bounds(n, world, rank, halo, C.byref(s), C.byref(l))
     return int(s.value), int(l.value)
+
+
+def device_count() -> int:
+    return int(lib().acwm_device_count())
+
+
+def search_host_sharded(matchers, text, cap: int | None = None, want_positions: bool = True,
+                        allow_overflow: bool = False):
+    """The multi-rank flow of main.c:464-656 in one process (``acwm_search_host_sharded``): matchers[r] scans
+    shard r of the host text on its own device and host thread; returns (count, global sorted positions,
+    per-shard counts)."""
+    if hasattr(text, "data_ptr"):
+        ptr, n = text.data_ptr(), text.numel()
+    else:
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        ptr, n = text.ctypes.data, text.size
+    world = len(matchers)
+    hs = (C.c_void_p * world)(*[m._h for m in matchers])
+    count, nw = C.c_uint64(), C.c_uint64()
+    per = np.zeros(world, np.uint64)
+    if want_positions:
+        cap = int(cap if cap is not None else max(1, n))
+        pos = np.empty(cap, np.uint64)
+        pptr = pos.ctypes.data_as(C.c_void_p)
+    else:
+        cap, pos, pptr = 0, np.zeros(0, np.uint64), None
+    _check(lib().acwm_search_host_sharded(hs, world, C.c_void_p(ptr), n, C.byref(count), pptr, cap, C.byref(nw),
+                                          per.ctypes.data_as(_u64p)),
+           allow=(ERR_OVERFLOW,) if allow_overflow else ())
+    return int(count.value), pos[:int(nw.value)], per
 
 
 class Matcher:

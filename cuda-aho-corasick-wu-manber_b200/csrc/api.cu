@@ -7,8 +7,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hostpack.hpp"
@@ -343,7 +345,7 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		CU(cudaEventRecord(ev, mt->s_copy2));
 		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
 		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
-		if ((rc = launch_scan(mt, mt->d_raw, n_raw, 0, ci * chunk_tiles, (ci + 1) * chunk_tiles, want_positions, ci > 0, 0,
+		if ((rc = launch_scan(mt, mt->d_raw, n_raw, mt->host_report_from, ci * chunk_tiles, (ci + 1) * chunk_tiles, want_positions, ci > 0, 0,
 					 mt->s_scan, 0)))
 			return rc;
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
@@ -375,7 +377,7 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		CU(cudaEventRecord(ev, mt->s_copy));
 		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
 		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
-		if ((rc = launch_scan(mt, mt->d_text, n, 0, std::min(n_tiles, ci * chunk_tiles),
+		if ((rc = launch_scan(mt, mt->d_text, n, mt->host_report_from, std::min(n_tiles, ci * chunk_tiles),
 					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, 0, mt->s_scan, 1)))
 			return rc;
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
@@ -599,7 +601,7 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		CU(cudaEventRecord(ev, mt->s_copy));
 		CU(cudaStreamWaitEvent(mt->s_scan, ev, 0));
 		CU(cudaEventRecord(mt->ev_time[2 * ci], mt->s_scan));
-		if ((rc = launch_scan(mt, mt->d_text, n, 0, std::min(n_tiles, ci * chunk_tiles),
+		if ((rc = launch_scan(mt, mt->d_text, n, mt->host_report_from, std::min(n_tiles, ci * chunk_tiles),
 					 std::min(n_tiles, (ci + 1) * chunk_tiles), want_positions, ci > 0, 0, mt->s_scan)))
 			return rc;
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
@@ -775,6 +777,118 @@ void acwm_shard_bounds(uint64_t n, uint32_t world, uint32_t rank, uint32_t halo,
 		*start = s;
 	if (len)
 		*len = e > s ? e - s : 0;
+}
+
+constexpr uint32_t kMaxShards = 64;
+
+int acwm_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+// One host thread per shard: shard r = the MPI rank r of main.c:467-477, its matcher mts[r] (resident on whatever
+// device the caller uploaded it to; not uploaded yet -> device r mod #devices), its slice of the caller's text.
+int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uint8_t *text, uint64_t n, uint64_t *count,
+		uint64_t *positions, uint64_t cap, uint64_t *n_written, uint64_t *shard_counts) {
+	if (!mts || world == 0 || world > kMaxShards || (!text && n))
+		return set_error(ACWM_ERR_INVALID, "acwm_search_host_sharded: NULL argument or world not in 1..64");
+	uint32_t m_max = 0;
+	for (uint32_t r = 0; r < world; r++) {
+		if (!mts[r])
+			return set_error(ACWM_ERR_INVALID, "acwm_search_host_sharded: NULL matcher");
+		for (uint32_t q = 0; q < r; q++)
+			if (mts[q] == mts[r])
+				return set_error(ACWM_ERR_INVALID, "acwm_search_host_sharded: one matcher per shard (searches on a matcher are not concurrent)");
+		if (r == 0)
+			m_max = mts[r]->c.prm.m_max;
+		else if (mts[r]->ps.len != mts[0]->ps.len || mts[r]->ps.bytes != mts[0]->ps.bytes)
+			return set_error(ACWM_ERR_INVALID, "acwm_search_host_sharded: the matchers hold different pattern sets");
+	}
+	const int n_dev = acwm_device_count();
+	if (n_dev <= 0)
+		return set_error(ACWM_ERR_CUDA, "acwm_search_host_sharded: no CUDA device");
+	const bool want_positions = positions != nullptr && cap > 0;
+	struct Shard {
+		uint64_t start = 0, len = 0, count = 0, written = 0;
+		std::unique_ptr<uint64_t[]> pos;
+		int rc = ACWM_OK;
+		std::string err;
+	};
+	std::vector<Shard> sh(world);
+	unsigned hw = std::thread::hardware_concurrency();
+	if (hw == 0)
+		hw = 4;
+	auto run = [&](uint32_t r) {
+		Shard &s = sh[r];
+		acwm_matcher *mt = mts[r];
+		acwm_shard_bounds(n, world, r, m_max ? m_max - 1 : 0, &s.start, &s.len);
+		if (s.len < mt->c.prm.m_min)
+			return; // an empty tail shard (n not much larger than world): nothing can end in it
+		if (!mt->uploaded && (s.rc = do_upload(mt, (int) (r % (uint32_t) n_dev), 0))) {
+			s.err = acwm_last_error();
+			return;
+		}
+		if (world > 1 && !mt->packer) // the shards of one process share its cores
+			mt->packer = new HostPacker(std::max(1u, hw / world));
+		if (want_positions)
+			s.pos.reset(new uint64_t[cap]); // untouched pages cost nothing
+		// every match is reported by exactly one shard: ends below m_max-1 of a shard but the first belong to
+		// its predecessor (with equal-length patterns a plain scan does that by itself, main.c:467-477)
+		mt->host_report_from = r ? (uint64_t) (m_max - 1) : 0;
+		s.rc = acwm_search_host(mt, text + s.start, s.len, &s.count, s.pos.get(), want_positions ? cap : 0, &s.written);
+		mt->host_report_from = 0;
+		if (s.rc != ACWM_OK)
+			s.err = acwm_last_error();
+	};
+	{
+		std::vector<std::thread> th;
+		for (uint32_t r = 1; r < world; r++)
+			th.emplace_back(run, r);
+		run(0);
+		for (auto &t : th)
+			t.join();
+	}
+	// the MPI_Reduce(SUM) of main.c:656, and the gather of the positions: shards are in text order and each
+	// shard's positions are sorted, so concatenation (+ shard start) is globally sorted
+	uint64_t total = 0, w = 0;
+	int rc = ACWM_OK;
+	std::string err;
+	for (uint32_t r = 0; r < world; r++) {
+		const Shard &s = sh[r];
+		if (s.rc != ACWM_OK && s.rc != ACWM_ERR_OVERFLOW) {
+			if (rc == ACWM_OK || rc == ACWM_ERR_OVERFLOW) {
+				rc = s.rc;
+				err = "shard " + std::to_string(r) + ": " + s.err;
+			}
+			continue;
+		}
+		if (s.rc == ACWM_ERR_OVERFLOW && rc == ACWM_OK) {
+			rc = ACWM_ERR_OVERFLOW;
+			err = "shard " + std::to_string(r) + ": " + s.err;
+		}
+		total += s.count;
+		if (shard_counts)
+			shard_counts[r] = s.count;
+		if (want_positions) {
+			const uint64_t take = std::min<uint64_t>(s.written, cap - w);
+			for (uint64_t i = 0; i < take; i++)
+				positions[w + i] = s.pos[i] + s.start;
+			w += take;
+			if (take < s.count && rc == ACWM_OK) {
+				rc = ACWM_ERR_OVERFLOW;
+				err = "more matches than the positions buffer holds (the count is exact)";
+			}
+		}
+	}
+	if (count)
+		*count = total;
+	if (n_written)
+		*n_written = w;
+	return rc == ACWM_OK ? ACWM_OK : set_error(rc, err);
 }
 
 int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_t *bytes) {

@@ -70,5 +70,6 @@ struct acwm_matcher {
 	double last_kernel_s = 0;
 	uint64_t last_h2d_bytes = 0; // bytes of text the last acwm_search_host sent over the link
 	int last_want_positions = 0;
+	uint64_t host_report_from = 0; // acwm_search_host_sharded: match ends below it belong to the shard in front
 	unsigned long long launches = 0;
 };

@@ -3,6 +3,7 @@
  * caller-side allocation and initialisation of the flat tables, same report lines.
  *
  *   smatcher_main <ac|wm> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-data DIR [-c]] [-seed S]
+ *                 [-gpus G]
  *
  * It is the integration example of INTEGRATION.md (what a maintainer of the reference
  * links instead of the reference's own objects) and the small CLI equivalent of
@@ -16,6 +17,9 @@
  * are chosen the way the reference's select_data_file does (main.c:31-123: the text size
  * -n selects the corpus under DIR/text, patterns in DIR/pattern/<n>/<m>/<alphabet>/pattern);
  * -c draws the pattern set "with hits" from the text instead of reading it (main.c:49).
+ * -gpus G adds the multi-rank flow of main.c:464-656 in one process: G shards with an (m-1)-byte halo
+ * (MPI_Scatterv), one matcher and one host thread per shard, spread over the CUDA devices present
+ * (acwm_search_host_sharded), the counts summed (MPI_Reduce) and printed per rank and in total.
  *
  * Build:  gcc -O2 -I include examples/smatcher_main.c -L cuda-aho-corasick-wu-manber_b200 \
  *             -lacwm_b200 -Wl,-rpath,'$ORIGIN/../cuda-aho-corasick-wu-manber_b200' -o examples/smatcher_main
@@ -28,7 +32,7 @@
 #include "acwm.h" /* declares the smatcher.h entry points + cuda_acN / cuda_wmN */
 
 static void usage(void) {
-	fprintf(stderr, "usage: smatcher_main <ac|wm> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-data DIR [-c]] [-seed S]\n");
+	fprintf(stderr, "usage: smatcher_main <ac|wm> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-data DIR [-c]] [-seed S] [-gpus G]\n");
 	exit(2);
 }
 
@@ -58,7 +62,7 @@ static double now_s(void) {
 int main(int argc, char **argv) {
 	int m = 0, n = 0, p_size = 0, alphabet = 0, B = 3, i, j;
 	const char *text_file = NULL, *pattern_file = NULL, *data_root = NULL;
-	int create_data = 0;
+	int create_data = 0, gpus = 0;
 	unsigned long long seed = 0;
 	static char sel_text[4096], sel_pattern[4096];
 	if (argc < 2 || (strcmp(argv[1], "ac") && strcmp(argv[1], "wm")))
@@ -72,6 +76,7 @@ int main(int argc, char **argv) {
 		if (!strcmp(argv[i], "-text")) text_file = argv[i + 1];
 		if (!strcmp(argv[i], "-pattern")) pattern_file = argv[i + 1];
 		if (!strcmp(argv[i], "-data")) data_root = argv[i + 1];
+		if (!strcmp(argv[i], "-gpus")) gpus = atoi(argv[i + 1]);
 		if (!strcmp(argv[i], "-seed")) {
 			seed = (unsigned long long) atoll(argv[i + 1]);
 			rng_state ^= seed * 0x9E3779B97F4A7C15ull;
@@ -180,6 +185,44 @@ int main(int argc, char **argv) {
 		free(PREFIX_value);
 		free(PREFIX_index);
 		free(PREFIX_size);
+	}
+	if (gpus > 0) { /* the MPI ranks of main.c:464-656 as shards of one process */
+		acwm_matcher **mts = (acwm_matcher **) calloc((size_t) gpus, sizeof(acwm_matcher *));
+		uint64_t *per = (uint64_t *) calloc((size_t) gpus, sizeof(uint64_t));
+		uint64_t total = 0;
+		int rc = ACWM_OK, r;
+		const int n_dev = acwm_device_count();
+		for (r = 0; r < gpus && rc == ACWM_OK; r++) {
+			rc = acwm_build(use_ac ? ACWM_ALGO_AC : ACWM_ALGO_WM, pattern2, NULL, (uint32_t) m, (uint32_t) p_size,
+					(uint32_t) alphabet, NULL, &mts[r]);
+			if (rc == ACWM_OK && n_dev > 0)
+				rc = acwm_upload(mts[r], r % n_dev, 0);
+		}
+		if (rc == ACWM_OK) {
+			const double t = now_s();
+			rc = acwm_search_host_sharded(mts, (uint32_t) gpus, text, (uint64_t) n, &total, NULL, 0, NULL, per);
+			const double dt = now_s() - t;
+			if (rc == ACWM_OK) {
+				for (r = 0; r < gpus; r++) {
+					uint64_t start = 0, len = 0;
+					acwm_shard_bounds((uint64_t) n, (uint32_t) gpus, (uint32_t) r, (uint32_t) m - 1, &start, &len);
+					printf("rank %d device %d text [%llu, %llu) matches \t%llu\t gpuTime \t%f\n", r, n_dev ? r % n_dev : -1,
+							(unsigned long long) start, (unsigned long long) (start + len), (unsigned long long) per[r],
+							acwm_last_kernel_seconds(mts[r]));
+				}
+				printf("Total results: %llu.\n", (unsigned long long) total);
+				printf("timeScatterExecuteGather: %f.\n", dt);
+			}
+		}
+		if (rc != ACWM_OK)
+			fprintf(stderr, "sharded search failed: %s\n", acwm_last_error());
+		for (r = 0; r < gpus; r++)
+			if (mts[r])
+				acwm_free(mts[r]);
+		free(mts);
+		free(per);
+		if (rc != ACWM_OK)
+			return 1;
 	}
 	for (j = 0; j < p_size; j++)
 		free(pattern[j]);

@@ -198,6 +198,21 @@ const char *acwm_last_error(void);
  * end is start + e_local, so every match is found by exactly one shard. */
 void acwm_shard_bounds(uint64_t n, uint32_t world, uint32_t rank, uint32_t halo, uint64_t *start, uint64_t *len);
 
+/* CUDA devices this process sees (0 if none / no driver). */
+int acwm_device_count(void);
+
+/* The whole multi-rank flow of main.c in one call and one process: MPI_Scatterv of the text with an (m-1)-byte halo
+ * (main.c:464-488), the per-rank search (main.c:630-647) and MPI_Reduce(SUM) of the counts (main.c:656), plus the
+ * gather of the positions the reference never had.  mts[r] is the matcher of shard r (build one per shard from the
+ * same pattern set; upload each to the device it shall run on -- a matcher not uploaded yet goes to device
+ * r mod acwm_device_count(); several shards may share a device).  Shard r = acwm_shard_bounds(n, world, r, m_max-1);
+ * one host thread per shard runs acwm_search_host on its slice of `text` (pinned or pageable), so the copies and the
+ * scans of all devices overlap.  *count = sum over the shards (== the unsharded count), positions = global match
+ * ends, ascending (shards are in text order and each is sorted); shard_counts (may be NULL) receives the
+ * world per-shard counts.  Errors as acwm_search_host; ACWM_ERR_OVERFLOW if cap positions do not hold them all. */
+int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uint8_t *text, uint64_t n, uint64_t *count,
+		uint64_t *positions, uint64_t cap, uint64_t *n_written, uint64_t *shard_counts);
+
 /* Raw views of the compiled tables (tests and diagnostics).  `which` is one of the
  * ACWM_BLOB_* ids; returns ACWM_ERR_INVALID if this matcher has no such table. */
 enum {

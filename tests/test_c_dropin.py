@@ -72,3 +72,32 @@ def test_c_driver_selects_and_loads_a_corpus(acwm, oracle, tmp_path):
     want = oracle.set_search(pats, text)["count"]
     assert int(re.search(r"search_wm2 matches \t(\d+)\t", out).group(1)) == want
     assert int(re.search(r"Total results: (\d+)\.", out).group(1)) == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", [0, 1])
+def test_c_driver_multi_gpu_mode(acwm, oracle, tmp_path, idx):
+    """-gpus G: the MPI flow of main.c:464-656 as shards of one process; per-rank counts are those of the
+    reference's ranks and they sum to the unsharded count."""
+    _build(acwm)
+    case = RANDOM_CASES[idx]
+    name, algo, alphabet, p, m, n, opts = case
+    pats, text = make_case(case)
+    ref = oracle.set_search(pats, text)
+    tf, pf = tmp_path / "text.bin", tmp_path / "pattern.bin"
+    text.tofile(tf)
+    np.ascontiguousarray(pats).tofile(pf)
+    G = 3
+    out = subprocess.run([EXE, "ac" if algo == acwm.AC else "wm", "-m", str(m), "-n", str(text.size), "-p_size",
+                          str(p), "-alphabet", str(alphabet), "-text", str(tf), "-pattern", str(pf), "-gpus", str(G)],
+                         capture_output=True, text=True, check=True, timeout=300).stdout
+    totals = [int(x) for x in re.findall(r"Total results: (\d+)\.", out)]
+    assert totals == [ref["count"], ref["count"]], out  # the reference-shaped flow, then the sharded one
+    ranks = re.findall(r"rank (\d+) device (\d+) text \[(\d+), (\d+)\) matches \t(\d+)\t", out)
+    assert len(ranks) == G
+    for r, (rank, dev, lo, hi, cnt) in enumerate(ranks):
+        start, length = acwm.shard_bounds(text.size, G, r, m - 1)
+        assert (int(rank), int(lo), int(hi)) == (r, start, start + length)
+        first = start + m - 1
+        inside = (ref["positions"] >= first) & (ref["positions"] < start + length)
+        assert int(cnt) == int(inside.sum())

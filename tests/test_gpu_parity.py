@@ -252,6 +252,81 @@ def test_sharded_scans_sum_to_whole(acwm, oracle, torch_cuda, world):
         mt.close()
 
 
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_search_host_sharded_one_process(acwm, oracle, torch_cuda, world):
+    """acwm_search_host_sharded = Scatterv + per-rank search + Reduce of main.c:464-656 in one call: one matcher and
+    one host thread per shard, spread over the devices present (all on GPU 0 on a one-GPU box)."""
+    n_dev = acwm.device_count()
+    assert n_dev >= 1
+    for cname in ("c2_wm_dna_p1000_m16", "c4_wm_ascii_mixed_8_64", "c1_ac_dna_p100_m8"):
+        case = next(c for c in RANDOM_CASES if c[0] == cname)
+        name, algo, alphabet, p, m, n, opts = case
+        pats, text = make_case(case)
+        ref = oracle.set_search(pats, text)
+        mts = [acwm.Matcher(algo, pats, alphabet, **opts) for _ in range(world)]
+        for r, mt in enumerate(mts):
+            mt.upload(device=r % n_dev)
+        for rep in range(2):  # the second call reuses every buffer of the first
+            count, pos, per = acwm.search_host_sharded(mts, text, cap=max(1, ref["count"]))
+            assert count == ref["count"] and int(per.sum()) == count, (cname, world, count, ref["count"])
+            assert np.array_equal(pos, ref["positions"]), (cname, world)
+        # per-shard counts are those of the reference's ranks: ends e with start + m_max-1 <= e (first shard: all)
+        m_max = max(q.size for q in pats) if isinstance(pats, list) else pats.shape[1]
+        for r in range(world):
+            start, length = acwm.shard_bounds(text.size, world, r, m_max - 1)
+            lo = start + (m_max - 1 if r else 0)
+            inside = (ref["positions"] >= lo) & (ref["positions"] < start + length)
+            assert int(per[r]) == int(inside.sum()), (cname, world, r)
+        # count only, and too small a position buffer: the count stays exact
+        count, pos, _ = acwm.search_host_sharded(mts, text, want_positions=False)
+        assert count == ref["count"] and pos.size == 0
+        if ref["count"] > 2:
+            count, pos, _ = acwm.search_host_sharded(mts, text, cap=2, allow_overflow=True)
+            assert count == ref["count"] and np.array_equal(pos, ref["positions"][:2])
+        for mt in mts:
+            mt.close()
+    # one matcher handed in twice / different pattern sets are refused
+    a = acwm.Matcher(acwm.WM, np.zeros((1, 8), np.uint8), 4)
+    b = acwm.Matcher(acwm.WM, np.ones((1, 8), np.uint8), 4)
+    for bad in ([a, a], [a, b]):
+        with pytest.raises(acwm.AcwmError):
+            acwm.search_host_sharded(bad, np.zeros(1000, np.uint8), cap=10)
+    a.close()
+    b.close()
+
+
+def test_search_host_sharded_packed_shards(acwm, oracle, torch_cuda):
+    """Shards large enough for the host packer (and, from pinned memory, for the hybrid raw + packed transfer): the
+    ends a shard leaves to its predecessor (mixed-length patterns: report_from = m_max - 1) are dropped on these
+    paths too."""
+    import os
+    import torch
+    dg = __import__("acwm_pkg").submodule("datagen")
+    base = dg.text_host((17 << 20) + 1000, 4, 43)
+    n_dev = acwm.device_count()
+    monkey = os.environ.get("ACWM_HOST_PACK")
+    os.environ["ACWM_HOST_PACK"] = "2"
+    try:
+        for algo, p, m in ((acwm.WM, 300, (8, 64)), (acwm.AC, 100, 8)):
+            pats = (dg.mixed_patterns_with_hits(base, p, m[0], m[1], 4, 9) if isinstance(m, tuple)
+                    else dg.patterns_with_hits(base, p, m, 4, 9))
+            mts = [acwm.Matcher(algo, pats, 4).upload(device=r % n_dev) for r in range(2)]
+            ref = oracle.set_search(pats, base)
+            count, pos, per = acwm.search_host_sharded(mts, base, cap=max(1, ref["count"]))
+            assert count == ref["count"] and np.array_equal(pos, ref["positions"]), (algo, p, m)
+            pinned = torch.from_numpy(np.concatenate([base] * 9)[: (150 << 20) + 77]).pin_memory()
+            ref = oracle.set_search(pats, pinned.numpy())
+            count, pos, per = acwm.search_host_sharded(mts, pinned, cap=max(1, ref["count"]))
+            assert count == ref["count"] and np.array_equal(pos, ref["positions"]), (algo, p, m, "pinned")
+            for mt in mts:
+                mt.close()
+    finally:
+        if monkey is None:
+            os.environ.pop("ACWM_HOST_PACK", None)
+        else:
+            os.environ["ACWM_HOST_PACK"] = monkey
+
+
 def test_overflow_and_bad_text(acwm, torch_cuda):
     text = np.zeros(10_000, np.uint8)
     mt = acwm.Matcher(acwm.AC, np.zeros((1, 4), np.uint8), 4)
