@@ -45,8 +45,8 @@ def main():
         print(json.dumps({"what": "acwm_search_host_sharded e2e (pinned host text -> host count + positions)",
                           "workload": a.workload, "gpus": G, "text_bytes": int(text.numel()), "best_s": best,
                           "GBps": text.numel() / best / 1e9, "count": count, "counts_equal": len(counts) == 1,
-                          "h2d_bytes": [int(mt.last_h2d_bytes()) for mt in mts],
-                          "kernel_s": [mt.last_kernel_seconds() for mt in mts]}), flush=True)
+                          "h2d_bytes": [int(mt.last_h2d_bytes) for mt in mts],
+                          "kernel_s": [mt.last_kernel_seconds for mt in mts]}), flush=True)
         for mt in mts:
             mt.close()
         del text
