@@ -254,11 +254,18 @@ constexpr unsigned kHostPackMinThreads = 10;
 constexpr uint64_t kPackChunk = 56 * HostPacker::kPieceSymbols; // 14 Mi symbols = 4096 tiles = 56 work items
 constexpr unsigned kPackRing = 16;
 static_assert(kPackChunk % kTile == 0 && kPackChunk % 64 == 0, "chunks are whole tiles and whole 16-byte pieces");
-// ACWM_HOST_RAW_PERCENT: share of a pinned host text that is sent unpacked beside the packed rest (default 30; 0 = none)
-static unsigned host_raw_percent() {
+// Share (percent) of a pinned host text that is sent unpacked beside the packed rest.  ACWM_HOST_RAW_PERCENT sets it
+// (0 = none); by default it follows the packer's thread count: link time n(r + (1-r)/4)/L and packing time n(1-r)/P
+// meet at r = (1/P - 1/4L) / (3/4L + 1/P), with P = 5.2 GB/s per packer thread on text that comes from DRAM and
+// L = 56 GB/s for the link (fit on the 16-core box, profiles/README.md session q: 15 threads -> 32 %, where 30 % beat
+// 22 % by 10 %; a text that is still in the host's caches packs faster and would take less).  Kept within 10..35 %.
+static unsigned host_raw_percent(unsigned threads) {
 	const char *e = getenv("ACWM_HOST_RAW_PERCENT");
-	const long v = e && *e ? atol(e) : 30;
-	return (unsigned) std::min<long>(std::max<long>(v, 0), 90);
+	if (e && *e)
+		return (unsigned) std::min<long>(std::max<long>(atol(e), 0), 90);
+	const double P = 5.2 * std::max(1u, threads), L = 56.0;
+	const double r = (1.0 / P - 0.25 / L) / (0.75 / L + 1.0 / P);
+	return (unsigned) std::min(35.0, std::max(10.0, 100.0 * r + 0.5));
 }
 // ACWM_HOST_PACK: 0 = never, 2 = always (tests), unset / 1 = when the host has the cores for it
 static int host_pack_mode() {
@@ -310,16 +317,17 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		HostPacker &p;
 		~Release() { p.finish(); }
 	} release{pk};
-	// The link moves raw text by DMA while the cores pack: a prefix of the text (whole chunks, ~30 %: about where link
-	// time and packing time meet at ~50 GB/s raw and ~93 GB/s packing) goes one byte per symbol from the caller's
+	// The link moves raw text by DMA while the cores pack: a prefix of the text (whole chunks, host_raw_percent: about
+	// where link time and packing time meet) goes one byte per symbol from the caller's
 	// PINNED buffer on a second copy stream, the rest is packed.  The packed part brings its own history (the 64-symbol
 	// halo of its first tile and the reach of the longest pattern's compare), packed by this thread.
 	uint64_t R = 0;
 	const uint32_t H = (std::max<uint32_t>(64u, mt->c.prm.m_max) + 63u) & ~63u;
-	if (n_chunks >= 5 && H <= 4096 && host_raw_percent() > 0) {
+	const unsigned raw_pct = host_raw_percent(mt->packer->threads());
+	if (n_chunks >= 5 && H <= 4096 && raw_pct > 0) {
 		cudaPointerAttributes at;
 		if (cudaPointerGetAttributes(&at, text) == cudaSuccess && at.type == cudaMemoryTypeHost)
-			R = std::min<uint64_t>(n_chunks - 1, (n_chunks * host_raw_percent() + 50) / 100);
+			R = std::min<uint64_t>(n_chunks - 1, (n_chunks * raw_pct + 50) / 100);
 		(void) cudaGetLastError();
 	}
 	const uint64_t n_raw = R * kPackChunk;
@@ -857,6 +865,12 @@ int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uin
 	uint64_t total = 0, w = 0;
 	int rc = ACWM_OK;
 	std::string err;
+	struct Move {
+		uint64_t *to;
+		const uint64_t *from;
+		uint64_t n, add;
+	};
+	std::vector<Move> moves;
 	for (uint32_t r = 0; r < world; r++) {
 		const Shard &s = sh[r];
 		if (s.rc != ACWM_OK && s.rc != ACWM_ERR_OVERFLOW) {
@@ -875,8 +889,8 @@ int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uin
 			shard_counts[r] = s.count;
 		if (want_positions) {
 			const uint64_t take = std::min<uint64_t>(s.written, cap - w);
-			for (uint64_t i = 0; i < take; i++)
-				positions[w + i] = s.pos[i] + s.start;
+			if (take) // (to, from, how many, what to add): copied below, one thread per shard when there is much to move
+				moves.push_back({positions + w, s.pos.get(), take, s.start});
 			w += take;
 			if (take < s.count && rc == ACWM_OK) {
 				rc = ACWM_ERR_OVERFLOW;
@@ -884,6 +898,20 @@ int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uin
 			}
 		}
 	}
+	auto move = [](const Move &mv) {
+		for (uint64_t i = 0; i < mv.n; i++)
+			mv.to[i] = mv.from[i] + mv.add;
+	};
+	if (w >= (1u << 20) && moves.size() > 1) {
+		std::vector<std::thread> th;
+		for (size_t i = 1; i < moves.size(); i++)
+			th.emplace_back(move, moves[i]);
+		move(moves[0]);
+		for (auto &t : th)
+			t.join();
+	} else
+		for (const Move &mv : moves)
+			move(mv);
 	if (count)
 		*count = total;
 	if (n_written)

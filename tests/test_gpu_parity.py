@@ -178,15 +178,17 @@ def test_host_text_packed_on_the_host(acwm, oracle, torch_cuda):
     import os
     dg = __import__("acwm_pkg").submodule("datagen")
     base = dg.text_host((17 << 20) + 1000, 4, 41)
-    monkey = os.environ.get("ACWM_HOST_PACK")
+    saved = {k: os.environ.get(k) for k in ("ACWM_HOST_PACK", "ACWM_HOST_RAW_PERCENT")}
     os.environ["ACWM_HOST_PACK"] = "2"  # also on a box with few cores
+    os.environ["ACWM_HOST_RAW_PERCENT"] = "30"  # the default follows the core count (none on a many-core box)
     try:
         _host_packed_cases(acwm, oracle, dg, base)
     finally:
-        if monkey is None:
-            os.environ.pop("ACWM_HOST_PACK", None)
-        else:
-            os.environ["ACWM_HOST_PACK"] = monkey
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def _host_packed_cases(acwm, oracle, dg, base):
@@ -285,6 +287,16 @@ def test_search_host_sharded_one_process(acwm, oracle, torch_cuda, world):
             assert count == ref["count"] and np.array_equal(pos, ref["positions"][:2])
         for mt in mts:
             mt.close()
+    if world == 3:  # > 1 Mi positions: the gather runs one thread per shard
+        text = np.zeros(1_500_000, np.uint8)
+        text[700_000] = 1
+        pats = np.zeros((1, 8), np.uint8)
+        mts = [acwm.Matcher(acwm.AC, pats, 4).upload(device=r % n_dev) for r in range(world)]
+        ref = oracle.set_search(pats, text)
+        count, pos, per = acwm.search_host_sharded(mts, text, cap=text.size)
+        assert count == ref["count"] > (1 << 20) and np.array_equal(pos, ref["positions"])
+        for mt in mts:
+            mt.close()
     # one matcher handed in twice / different pattern sets are refused
     a = acwm.Matcher(acwm.WM, np.zeros((1, 8), np.uint8), 4)
     b = acwm.Matcher(acwm.WM, np.ones((1, 8), np.uint8), 4)
@@ -304,8 +316,9 @@ def test_search_host_sharded_packed_shards(acwm, oracle, torch_cuda):
     dg = __import__("acwm_pkg").submodule("datagen")
     base = dg.text_host((17 << 20) + 1000, 4, 43)
     n_dev = acwm.device_count()
-    monkey = os.environ.get("ACWM_HOST_PACK")
+    saved = {k: os.environ.get(k) for k in ("ACWM_HOST_PACK", "ACWM_HOST_RAW_PERCENT")}
     os.environ["ACWM_HOST_PACK"] = "2"
+    os.environ["ACWM_HOST_RAW_PERCENT"] = "30"
     try:
         for algo, p, m in ((acwm.WM, 300, (8, 64)), (acwm.AC, 100, 8)):
             pats = (dg.mixed_patterns_with_hits(base, p, m[0], m[1], 4, 9) if isinstance(m, tuple)
@@ -321,10 +334,11 @@ def test_search_host_sharded_packed_shards(acwm, oracle, torch_cuda):
             for mt in mts:
                 mt.close()
     finally:
-        if monkey is None:
-            os.environ.pop("ACWM_HOST_PACK", None)
-        else:
-            os.environ["ACWM_HOST_PACK"] = monkey
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def test_overflow_and_bad_text(acwm, torch_cuda):
