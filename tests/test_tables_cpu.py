@@ -140,6 +140,19 @@ def test_no_cpu_fallback_without_gpu(acwm):
     with pytest.raises(acwm.AcwmError) as e:
         mt.search_host(np.zeros(100, np.uint8))
     assert e.value.code == acwm.ERR_CUDA
+    # the one-process multi-GPU flow too; its argument checks come first
+    assert acwm.device_count() == 0
+    mts = [acwm.Matcher(acwm.AC, np.zeros((1, 4), np.uint8), 4) for _ in range(2)]
+    with pytest.raises(acwm.AcwmError) as e:
+        acwm.search_host_sharded(mts, np.zeros(100, np.uint8))
+    assert e.value.code == acwm.ERR_CUDA
+    with pytest.raises(acwm.AcwmError) as e:
+        acwm.search_host_sharded([mts[0], mts[0]], np.zeros(100, np.uint8))
+    assert e.value.code == acwm.ERR_INVALID
+    other = acwm.Matcher(acwm.AC, np.ones((1, 4), np.uint8), 4)
+    with pytest.raises(acwm.AcwmError) as e:
+        acwm.search_host_sharded([mts[0], other], np.zeros(100, np.uint8))
+    assert e.value.code == acwm.ERR_INVALID
 
 
 def test_product_never_imports_oracle():
