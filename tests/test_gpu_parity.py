@@ -191,6 +191,37 @@ def test_host_text_packed_on_the_host(acwm, oracle, torch_cuda):
                 os.environ[k] = v
 
 
+def test_hybrid_transfer_raw_share_variants(acwm, oracle, torch_cuda):
+    """The raw share of the hybrid host transfer follows the host's core count (csrc/api.cu host_raw_percent): every
+    split of a pinned text into raw chunks + packed rest gives the oracle's count and positions."""
+    import os
+    import torch
+    dg = __import__("acwm_pkg").submodule("datagen")
+    base = dg.text_host((15 << 20) + 333, 4, 47)
+    pinned = torch.from_numpy(np.concatenate([base] * 6)[: (88 << 20) + 1001]).pin_memory()  # 7 chunks of 14 Mi
+    saved = {k: os.environ.get(k) for k in ("ACWM_HOST_PACK", "ACWM_HOST_RAW_PERCENT")}
+    os.environ["ACWM_HOST_PACK"] = "2"
+    try:
+        for algo, p, m in ((acwm.WM, 1000, 16), (acwm.AC, 100, 8), (acwm.WM, 300, (8, 64))):
+            pats = (dg.mixed_patterns_with_hits(base, p, m[0], m[1], 4, 11) if isinstance(m, tuple)
+                    else dg.patterns_with_hits(base, p, m, 4, 11))
+            mt = acwm.Matcher(algo, pats, 4)
+            ref = oracle.set_search(pats, pinned.numpy())
+            for pct in (5, 10, 35, 60, 90):  # 0 / 1 / 2 / 4 / 6 raw chunks
+                os.environ["ACWM_HOST_RAW_PERCENT"] = str(pct)
+                count, pos = mt.search_host(pinned, cap=max(1, ref["count"]))
+                assert count == ref["count"] and np.array_equal(pos, ref["positions"]), (algo, p, m, pct)
+                raw_chunks = min(6, (7 * pct + 50) // 100)
+                assert mt.last_h2d_bytes > pinned.numel() // 4 + raw_chunks * (14 << 20) * 3 // 4 - 4096, (pct, mt.last_h2d_bytes)
+            mt.close()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def _host_packed_cases(acwm, oracle, dg, base):
     cases = [(acwm.AC, 100, 8, {}), (acwm.WM, 1000, 16, {}), (acwm.AC, 1000, 16, {}), (acwm.WM, 20000, 32, {}),
              (acwm.AC, 3, 70, {}), (acwm.WM, 300, (8, 64), {})]
