@@ -9,6 +9,8 @@
 #include <ctime>
 #include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -842,8 +844,14 @@ int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uin
 		}
 		if (world > 1 && !mt->packer) // the shards of one process share its cores
 			mt->packer = new HostPacker(std::max(1u, hw / world));
-		if (want_positions)
-			s.pos.reset(new uint64_t[cap]); // untouched pages cost nothing
+		if (want_positions) {
+			s.pos.reset(new (std::nothrow) uint64_t[cap]); // untouched pages cost nothing
+			if (!s.pos) {
+				s.rc = ACWM_ERR_NOMEM;
+				s.err = "no host memory for the shard's positions";
+				return;
+			}
+		}
 		// every match is reported by exactly one shard: ends below m_max-1 of a shard but the first belong to
 		// its predecessor (with equal-length patterns a plain scan does that by itself, main.c:467-477)
 		mt->host_report_from = r ? (uint64_t) (m_max - 1) : 0;
@@ -853,10 +861,27 @@ int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uin
 			s.err = acwm_last_error();
 	};
 	{
+		// no exception leaves the C ABI: a shard whose thread cannot be started runs on this one
+		auto guarded = [&](uint32_t r) {
+			try {
+				run(r);
+			} catch (const std::exception &e) {
+				sh[r].rc = ACWM_ERR_NOMEM;
+				sh[r].err = e.what();
+			}
+		};
 		std::vector<std::thread> th;
-		for (uint32_t r = 1; r < world; r++)
-			th.emplace_back(run, r);
-		run(0);
+		th.reserve(world);
+		std::vector<uint32_t> here{0};
+		for (uint32_t r = 1; r < world; r++) {
+			try {
+				th.emplace_back(guarded, r);
+			} catch (const std::exception &) {
+				here.push_back(r);
+			}
+		}
+		for (uint32_t r : here)
+			guarded(r);
 		for (auto &t : th)
 			t.join();
 	}
@@ -904,9 +929,15 @@ int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uin
 	};
 	if (w >= (1u << 20) && moves.size() > 1) {
 		std::vector<std::thread> th;
-		for (size_t i = 1; i < moves.size(); i++)
-			th.emplace_back(move, moves[i]);
+		th.reserve(moves.size());
 		move(moves[0]);
+		for (size_t i = 1; i < moves.size(); i++) {
+			try {
+				th.emplace_back(move, moves[i]);
+			} catch (const std::exception &) {
+				move(moves[i]);
+			}
+		}
 		for (auto &t : th)
 			t.join();
 	} else
