@@ -2,19 +2,24 @@
 """Bench harness for the AC / WM scan path (contract: see the task statement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|c1|...] [--text-mib M]
+                    [--workload c1+c2|c1|c2|...] [--text-mib M] [--no-big-legs]
 
-One JSON line on rank 0.  A "step" is one pass of the hot path over one batch of
-synthetic text: default workload = BASELINE.json configs[1] (Wu-Manber, 128 MiB 4-symbol
-DNA text, 1000 patterns of m = 16), per GPU (weak scaling: every rank scans its own
-128 MiB shard + (m-1)-byte halo, counts are all-reduced over NCCL).
+One JSON line on rank 0.  BASELINE.json's metric is "text GB/s scanned (AC & WM)", so the default
+run measures BOTH algorithms in one invocation: leg AC = BASELINE configs[0] (Aho-Corasick, 100
+patterns of m = 8) and leg WM = configs[1] (Wu-Manber, 1000 patterns of m = 16), both on the same
+128 MiB 4-symbol DNA text per GPU (weak scaling: every rank scans its own 128 MiB shard + (m-1)-byte
+halo; only the 8-byte counts cross NVLink).  A "step" is one pass of one algorithm over one text.
+Top-level `value` = the LOWER of the two legs (ms_per_step / roofline / e2e / cpu_baseline are that
+leg's); `per_algo` carries every number of both.
 
  value   text GB/s, text resident in HBM, CUDA events on the launching stream, max over ranks
  e2e     same metric through acwm_search_host with the text in PINNED HOST memory:
          H2D of the text and D2H of count + positions inside the timed region
- roofline  the scan kernel (CUDA events inside acwm_scan_device), algorithmic bytes =
-         1 B per text symbol + 8 B per reported position, vs the measured HBM peak
- cpu_baseline  the unmodified reference search_wu / search_ac (oracle/_ref) on all host cores
+ roofline  the scan kernel: algorithmic bytes = 1 B per text symbol + 8 B per reported position,
+         over the average launch duration in the timed region, vs the measured HBM peak
+ cpu_baseline  the unmodified reference search_ac / search_wu (oracle/_ref) on all host cores
+ north_star_legs  the same two algorithms on 1 GiB of DNA per GPU and BASELINE configs[2]
+         (AC, 100 000 patterns of m = 32, 10^9 bytes per GPU): what the north star scales on
 """
 import argparse
 import json
@@ -39,6 +44,7 @@ WORKLOADS = {
     "ac10k16": ("AC", 4, 10000, 16, "Aho-Corasick, DNA, 10000 patterns m=16 (sweep point)"),
     "c4": ("WM", 256, 10000, (8, 64), "BASELINE configs[3]: Wu-Manber, 256-symbol text, 10000 patterns m=8..64"),
 }
+DEFAULT_WORKLOAD = "c1+c2"
 TEXT_SEED, PAT_SEED = 1, 2
 N_ROTATE = 4  # distinct text buffers per rank, cycled so that no step finds its text in L2
 
@@ -51,6 +57,23 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(workload, n):
+    """The `config` object: names the workload, identical in both arms (ours / reference)."""
+    legs = workload.split("+")
+    algos = {}
+    for wl in legs:
+        algo, alphabet, p, m, desc = WORKLOADS[wl]
+        algos[algo if len(legs) > 1 else wl] = {"workload": wl, "algo": algo, "patterns": p,
+                                               "m": list(m) if isinstance(m, tuple) else m, "alphabet": alphabet,
+                                               "what": desc}
+    if workload == DEFAULT_WORKLOAD:
+        name = (f"c1+c2: BASELINE configs[0] (AC, 100 patterns m=8) and configs[1] (WM, 1000 patterns m=16, B=3), "
+                f"each over the same {n >> 20} MiB 4-symbol DNA text per GPU; value = the slower of the two")
+    else:
+        name = " + ".join(f"{wl}: {WORKLOADS[wl][4]}" for wl in legs)
+    return {"workload": name, "text_bytes_per_gpu": n, "legs": algos}
 
 
 class ClockSampler(threading.Thread):
@@ -85,14 +108,14 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.005)
 
-    def summary(self, t0, t1):
+    def summary(self, windows):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
         nv = self.nv
-        inside = [s for s in self.samples if t0 <= s[0] <= t1]
-        window = "timed region"
+        inside = [s for s in self.samples if any(t0 <= s[0] <= t1 for t0, t1 in windows)]
+        window = "timed regions"
         if len(inside) < 3:
-            inside, window = self.samples, "warm-up + timed + profiling loops (timed region < 3 samples)"
+            inside, window = self.samples, "warm-up + timed + profiling loops (timed regions < 3 samples)"
         names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
@@ -114,6 +137,11 @@ def make_patterns(dg, text_np, wl):
     return dg.patterns_with_hits(text_np, p, m, alphabet, PAT_SEED), m
 
 
+def pick_limiting(per):
+    """The leg `value` is quoted on: the slower one."""
+    return min(per, key=lambda k: per[k]["value"])
+
+
 # ============================================================== reference arm (CPU)
 def run_reference(args):
     """The reference's own CPU implementation (oracle/_ref = unmodified ac.c / wu.c compiled
@@ -124,105 +152,221 @@ def run_reference(args):
     import oracle
     import acwm_pkg
     dg = acwm_pkg.submodule("datagen")
-    algo, alphabet, p, m, desc = WORKLOADS[args.workload]
+    legs = args.workload.split("+")
     n = args.text_mib << 20
     cores = os.cpu_count() or 1
-    text = dg.text_host(n, alphabet, TEXT_SEED)
-    pats, m_max = make_patterns(dg, text, args.workload)
-    mixed = isinstance(m, tuple)
-    use_ref = oracle.ref_available() and not mixed and not (algo == "AC" and p * m_max > 400_000)
+    texts = {}
+    per = {}
+    for wl in legs:
+        algo, alphabet, p, m, desc = WORKLOADS[wl]
+        if alphabet not in texts:
+            texts[alphabet] = dg.text_host(n, alphabet, TEXT_SEED)
+        text = texts[alphabet]
+        pats, m_max = make_patterns(dg, text, wl)
+        mixed = isinstance(m, tuple)
+        use_ref = oracle.ref_available() and not mixed and not (algo == "AC" and p * m_max > 400_000)
 
-    def one_pass(sample):
-        t0 = time.perf_counter()
-        if use_ref:
-            r = (oracle.ref_ac if algo == "AC" else oracle.ref_wu)(pats, alphabet, sample, threads=cores)
-            secs, cnt = r["search_s"], r["count"]
-        else:  # port: single scalar thread
-            r = oracle.set_search(pats, sample, want_positions=False)
-            secs, cnt = time.perf_counter() - t0, r["count"]
-        return secs, cnt
+        def one_pass(sample):
+            t0 = time.perf_counter()
+            if use_ref:
+                r = (oracle.ref_ac if algo == "AC" else oracle.ref_wu)(pats, alphabet, sample, threads=cores)
+                return r["search_s"], r["count"]
+            r = oracle.set_search(pats, sample, want_positions=False)  # port: single scalar thread
+            return time.perf_counter() - t0, r["count"]
 
-    # bounded sample: calibrate on 8 MiB, then size each step for a whole run of ~2 minutes
-    cal_secs, _ = one_pass(text[: min(n, 8 << 20)])
-    rate = min(n, 8 << 20) / max(cal_secs, 1e-6)
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    sample_n = int(min(n, max(1 << 20, rate * budget)))
-    sample = text[:sample_n]
-    for _ in range(args.warmup):
-        one_pass(sample)
-    tot = 0.0
-    for _ in range(args.steps):
-        s, cnt = one_pass(sample)
-        tot += s
-    value = sample_n * args.steps / tot / 1e9
-    kind = "reference" if use_ref else "port"
+        # bounded sample: calibrate on 8 MiB, then size each step for a whole run of ~2 minutes over all legs
+        cal_secs, _ = one_pass(text[: min(n, 8 << 20)])
+        rate = min(n, 8 << 20) / max(cal_secs, 1e-6)
+        budget = 120.0 / len(legs) / max(1, args.steps + args.warmup)
+        sample_n = int(min(n, max(1 << 20, rate * budget)))
+        sample = text[:sample_n]
+        for _ in range(args.warmup):
+            one_pass(sample)
+        tot = 0.0
+        for _ in range(args.steps):
+            s, cnt = one_pass(sample)
+            tot += s
+        value = sample_n * args.steps / tot / 1e9
+        kind = "reference" if use_ref else "port"
+        per[algo if len(legs) > 1 else wl] = {
+            "workload": wl, "value": value, "unit": "GB/s", "ms_per_step": tot / args.steps * 1e3,
+            "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores if use_ref else 1, "kind": kind,
+                             "sample": f"first {sample_n} bytes of the {n}-byte text per step (search only, "
+                                       f"preprocessing excluded as in main.c:246-262; unmodified "
+                                       f"search_{'ac' if algo == 'AC' else 'wu'}, {cores} threads, MPI-rank shard "
+                                       f"geometry of main.c:467-477)", "count": int(cnt)},
+            "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+    lim = pick_limiting(per)
     line = {
-        "impl": "reference", "metric": "text GB/s scanned", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3,
+        "impl": "reference", "metric": "text GB/s scanned", "value": per[lim]["value"], "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per[lim]["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "text_bytes_per_gpu": n, "algo": algo, "patterns": p,
-                   "m": m_max if not mixed else list(m), "alphabet": alphabet},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores if use_ref else 1, "kind": kind,
-                         "sample": f"first {sample_n} bytes of the {n}-byte text per step "
-                                   f"(search only, preprocessing excluded as in main.c:246-262)"},
-        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "config": workload_config(args.workload, n),
+        "value_is": f"the slower leg ({lim})", "per_algo": per,
+        "cpu_baseline": per[lim]["cpu_baseline"], "e2e": per[lim]["e2e"], "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
 # ============================================================== our arm (GPU)
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def pin_rank_to_cores(local_rank, local_world):
+    """One process per GPU on one box: give every rank its own slice of the host cores, on the NUMA node of its GPU
+    when the topology can be read (pinned buffers are then allocated node-local, first touch).  Returns a dict for
+    the report."""
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+    except Exception:
+        return {"pinned": False}
+    if local_world <= 1 or len(avail) < 2 * local_world:
+        return {"pinned": False, "cores": len(avail)}
+    node_of = {}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        for g in range(local_world):
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(g)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]
+            node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+            node_of[g] = max(node, 0)
+    except Exception:
+        node_of = {g: 0 for g in range(local_world)}
 
-    import acwm_pkg
-    acwm = acwm_pkg.load()
-    dg = acwm_pkg.submodule("datagen")
-    sh = acwm_pkg.submodule("sharding")
+    def cpus_of(node):
+        try:
+            out = []
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                out.extend(range(int(a), int(b or a) + 1))
+            return [c for c in out if c in avail]
+        except Exception:
+            return []
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    node = node_of.get(local_rank, 0)
+    mates = [g for g in range(local_world) if node_of.get(g, 0) == node]
+    cpus = cpus_of(node)
+    if len(cpus) < 2 * len(mates):  # topology unreadable or lopsided: plain equal slices of what we may use
+        mates, cpus = list(range(local_world)), avail
+    k = len(cpus) // len(mates)
+    i = mates.index(local_rank)
+    mine = cpus[i * k:(i + 1) * k]
+    try:
+        os.sched_setaffinity(0, mine)
+    except Exception:
+        return {"pinned": False, "cores": len(avail)}
+    return {"pinned": True, "numa_node": node, "cores": len(mine), "first_core": mine[0]}
 
-    algo_name, alphabet, p, m, desc = WORKLOADS[args.workload]
+
+def measure_pinned_copy(torch, dev, nbytes=256 << 20):
+    """The box's own H2D rate for this rank's link (pinned host -> HBM, cudaMemcpyAsync): the ceiling of e2e when the
+    text crosses the link one byte per symbol."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    src.zero_()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return 3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
+class Rig:
+    """What the legs of one process share: the process group, texts by (alphabet, size), the clock sampler."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import acwm_pkg
+        self.torch, self.dist = torch, dist
+        self.acwm = acwm_pkg.load()
+        self.dg = acwm_pkg.submodule("datagen")
+        self.sh = acwm_pkg.submodule("sharding")
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.affinity = pin_rank_to_cores(self.local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(self.world))))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.texts = {}
+        self.timed_windows = []
+        self.sampler = ClockSampler(self.local_rank)
+        self.sampler.start()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x), [float(x)]
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        g = [self.torch.zeros(1, dtype=self.torch.float64, device=self.dev) for _ in range(self.world)]
+        self.dist.all_gather(g, t)
+        per = [float(v.item()) for v in g]
+        return max(per), per
+
+    def text_set(self, alphabet, n, halo, host_copies):
+        """N_ROTATE distinct shards per rank, resident in HBM (+ `host_copies` of them on the host).  Buffer 0 of rank
+        r is shard r of the global text = concatenation of the per-rank texts (seed TEXT_SEED + r), followed by the
+        first m_max-1 bytes of shard r+1 (the halo of main.c:467-477); the others only defeat L2.  Texts much larger
+        than L2 (126 MB) need no rotation: every step streams from HBM anyway, and are generated on the device."""
+        if self.rank + 1 >= self.world:
+            halo = 0  # the last shard (and a single GPU) has no successor to borrow a halo from
+        key = (alphabet, n, halo)
+        if key in self.texts:
+            return self.texts[key]
+        torch, dg, rank, world = self.torch, self.dg, self.rank, self.world
+        if n <= (256 << 20):
+            def shard(k):
+                own = dg.text_host(n, alphabet, TEXT_SEED + rank + 1000 * k)
+                if rank + 1 < world and halo:
+                    own = np.concatenate([own, dg.text_host(n, alphabet, TEXT_SEED + rank + 1 + 1000 * k)[:halo]])
+                return own
+            host = [shard(k) for k in range(N_ROTATE)]
+            devt = [torch.from_numpy(t).to(self.dev) for t in host]
+            host = host[:max(host_copies, 1)]
+        else:
+            devt = [dg.text_device(n + (halo if rank + 1 < world else 0), alphabet, TEXT_SEED + rank, self.dev)]
+            host = []
+        self.texts = {key: (host, devt)}  # one set at a time stays resident
+        return host, devt
+
+
+def run_leg(rig, wl, n, steps, warmup, full=True, pats=None):
+    """One workload on every rank's shard: timed device-resident loop (+ isolated launches, e2e and the CPU baseline
+    when `full`).  Returns the leg's report (rank 0) -- every rank must call it (collectives inside)."""
+    torch, dist, acwm, dg, sh, args = rig.torch, rig.dist, rig.acwm, rig.dg, rig.sh, rig.args
+    world, rank, dev, stream = rig.world, rig.rank, rig.dev, rig.stream
+    algo_name, alphabet, p, m, desc = WORKLOADS[wl]
     algo = acwm.AC if algo_name == "AC" else acwm.WM
-    n = args.text_mib << 20  # per-GPU shard (weak scaling)
-
-    # the pattern set is the same on every rank (replicated tables): "with hits" from rank 0's text
-    text0 = dg.text_host(n, alphabet, TEXT_SEED)
-    pats, m_max = make_patterns(dg, text0, args.workload)
+    m_max = m[1] if isinstance(m, tuple) else m
     halo = m_max - 1
+    host_texts, dev_texts = rig.text_set(alphabet, n, halo, 2 if full else 1)
+    nrot = len(dev_texts)
+    # the pattern set is the same on every rank (replicated tables): "with hits" from rank 0's first text
+    if pats is None:
+        text0 = host_texts[0] if (host_texts and rank == 0 and world == 1) else dg.text_host(min(n, 128 << 20), alphabet, TEXT_SEED)
+        pats, _ = make_patterns(dg, text0, wl)
+    t_build = time.perf_counter()
     mt = acwm.Matcher(algo, pats, alphabet, **json.loads(args.matcher_opts))
+    t_build = time.perf_counter() - t_build
     pos_cap = max(1 << 20, n // 16)
-    mt.upload(local_rank, pos_cap)
-
-    # N_ROTATE distinct shards per rank.  Buffer 0 of rank r is shard r of the global text
-    # = concatenation of the per-rank texts (seed TEXT_SEED + r), followed by the first
-    # m_max-1 bytes of shard r+1 (the halo of main.c:467-477); the others only defeat L2.
-    def shard_text(seed_base, k):
-        own = dg.text_host(n, alphabet, seed_base + rank + 1000 * k)
-        if rank + 1 < world and halo:
-            nxt = dg.text_host(n, alphabet, seed_base + rank + 1 + 1000 * k)[:halo]
-            own = np.concatenate([own, nxt])
-        return own
-
-    # texts much larger than L2 (126 MB) need no rotation: every step streams from HBM anyway
-    N_ROTATE = globals()["N_ROTATE"] if n <= (256 << 20) else 1
-    host_texts = [text0 if (rank == 0 and world == 1) else shard_text(TEXT_SEED, 0)]
-    for k in range(1, N_ROTATE):
-        host_texts.append(shard_text(TEXT_SEED, k))
-    dev_texts = [torch.from_numpy(t).to(dev) for t in host_texts]
+    mt.upload(rig.local_rank, pos_cap)
     report_from = halo if rank > 0 else 0
-    stream = torch.cuda.current_stream().cuda_stream
     count_buf = torch.zeros(1, dtype=torch.int64, device=dev)
     d_count_ptr, _ = mt.result_device_ptrs()
-
     count_view = _device_count_tensor(torch, d_count_ptr, dev)  # the matcher's device-resident count
 
     # the only thing that crosses NVLink is the per-GPU match count (8 bytes): exchanged inside the scan
@@ -230,160 +374,195 @@ def run_ours(args):
     fused_exchange = world > 1 and not args.nccl_count and sh.connect_peers(mt, dev)
 
     def step(i, want_positions=True):
-        mt.scan_tensor(dev_texts[i % N_ROTATE], want_positions=want_positions, report_from=report_from)
+        mt.scan_tensor(dev_texts[i % nrot], want_positions=want_positions, report_from=report_from)
         if world > 1 and not fused_exchange:
             count_buf.copy_(count_view)
             sh.allreduce_count_tensor(count_buf)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     mt.set_overlap(not args.no_overlap)  # consecutive scans of resident texts: programmatic dependent launches
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
-    barrier()
+    rig.barrier()
     launches0 = mt.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
     ev1.record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    rig.barrier()
+    rig.timed_windows.append((t_wall0, time.perf_counter()))
     launches = mt.launch_count - launches0
-    per_rank_ms = [elapsed_ms / args.steps]
-    if world > 1:
-        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
-        dist.all_gather(gathered, torch.tensor([elapsed_ms], dtype=torch.float64, device=dev))
-        per_rank_ms = [float(g.item()) / args.steps for g in gathered]
-        elapsed_ms = max(per_rank_ms) * args.steps  # max over ranks
-    ms_per_step = elapsed_ms / args.steps
-    text_bytes = sum(int(dev_texts[(args.warmup + i) % N_ROTATE].numel()) for i in range(args.steps)) / args.steps
+    ms_per_step, per_rank_ms = rig.max_over_ranks(ev0.elapsed_time(ev1) / steps)  # max over ranks
+    text_bytes = sum(int(dev_texts[(warmup + i) % nrot].numel()) for i in range(steps)) / steps
     value = world * text_bytes / (ms_per_step * 1e-3) / 1e9
 
     # ---- results of the last step (parity of the global count is a test, here it is reported)
     mt.set_overlap(False)
-    last_count, last_pos, _ = mt.fetch(cap=pos_cap, stream=stream)
+    last_count, _, _ = mt.fetch(cap=pos_cap, stream=stream)
     global_count = sh.allreduce_count(last_count, dev)
     if fused_exchange:  # what the kernels exchanged must be what NCCL sums
         fused_global = mt.fetch_global_count(stream)
         assert fused_global == global_count, (fused_global, global_count)
         mt.set_peers(0, 0, None)  # the legs below are per-rank (profiling, e2e): no exchange
 
-    # ---- roofline: the scan kernel alone, CUDA events on the launching stream
+    # ---- the scan kernel alone: CUDA events around single launches on the launching stream
     mt.set_profiling(True)
-    scan_s, fin_s, matches = [], [], []
-    for i in range(max(args.steps, 8)):
-        mt.scan_tensor(dev_texts[i % N_ROTATE], want_positions=True, report_from=report_from)
-        a, b = mt.profiled_seconds()
+    scan_s, matches = [], []
+    for i in range(max(min(steps, 20), 8)):
+        mt.scan_tensor(dev_texts[i % nrot], want_positions=True, report_from=report_from)
+        a, _ = mt.profiled_seconds()
         c, _, _ = mt.fetch(cap=0, stream=stream)
         scan_s.append(a)
-        fin_s.append(b)
         matches.append(c)
     mt.set_profiling(False)
-    scan_isolated = float(np.mean(scan_s))
-    alg_bytes = float(np.mean([dev_texts[i % N_ROTATE].numel() + 8 * matches[i] for i in range(len(matches))]))
+    scan_isolated = float(np.mean(scan_s[2:]))
+    alg_bytes = float(np.mean([dev_texts[i % nrot].numel() + 8 * matches[i] for i in range(len(matches))]))
     peak, peak_src = peaks()
-    # the kernel's average launch duration over the timed region: at N = 1 a step IS one launch of the scan
-    # kernel and nothing else, so the timed region / K is that average (back-to-back launches); otherwise (a
-    # collective per step) the event-bracketed single launches are used
-    scan_mean = ms_per_step * 1e-3 if (world == 1 and launches == args.steps) else scan_isolated
+    # The kernel's average launch duration over the timed region.  A step is ONE launch of the scan kernel and nothing
+    # else whenever the count is exchanged inside the kernel (every N) -- then the timed region / K is that average;
+    # with a collective per step (--nccl-count, or no peer memory) the event-bracketed single launches are used.
+    one_launch_per_step = launches == steps
+    scan_mean = ms_per_step * 1e-3 if one_launch_per_step else scan_isolated
     achieved = alg_bytes / scan_mean / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get(wl, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    info = mt.info
+    rep = {
+        "workload": wl, "algo": algo_name, "value": value, "unit": "GB/s", "ms_per_step": ms_per_step,
+        "text_bytes_per_gpu": n, "gpu_launches": int(launches), "matches_last_step": int(global_count),
+        "per_rank_ms_per_step": [round(x, 5) for x in per_rank_ms],
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "scan_kernel (one launch: TMA-fed scan + barrier-free position ordering + count exchange)",
+                     "kernel_ms": scan_mean * 1e3, "kernel_ms_isolated_launch": scan_isolated * 1e3,
+                     "frac_isolated_launch": alg_bytes / scan_isolated / 1e9 / peak,
+                     "duration_source": "timed region / K (one launch per step)" if one_launch_per_step
+                     else "CUDA events around single launches (a collective per step)",
+                     "algorithmic_bytes_per_launch": alg_bytes, "frac_of_8TBps_spec": achieved / 8000.0},
+        "count_exchange": ("none (1 GPU)" if world == 1 else
+                           "in-kernel system-scope stores into NVLink peer mailboxes (torch symmetric memory)"
+                           if fused_exchange else "NCCL all_reduce of the 8-byte count per step"),
+        "kernel": {k: info[k] for k in ("packed2bit", "stride", "depth", "exact_front", "front_kind", "n_rows",
+                                         "table_in_smem", "smem_bytes", "threads", "stages", "ctas_per_sm")},
+        "table_build_s": round(t_build, 3),
+    }
+    if not full:
+        mt.close()
+        return rep
 
     # ---- end to end through the public API: pinned host text -> count + positions on the host
     pinned = [torch.from_numpy(t).pin_memory() for t in host_texts[:2]]
     if len(pinned) == 1:
         pinned = pinned * 2
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(steps, 10))
     pos_out = np.empty(pos_cap, np.uint64)  # the caller's position buffer, reused
     for i in range(2):
         mt.search_host(pinned[i % 2], out=pos_out)
-    barrier()
+    rig.barrier()
     t0 = time.perf_counter()
-    e2e_count = 0
+    counts = []
+    kernel_s = 0.0
     for i in range(e2e_steps):
-        c, ppos = mt.search_host(pinned[i % 2], out=pos_out)
-        if world > 1:
-            c = sh.allreduce_count(c, dev)
-        e2e_count = c
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        c, _ = mt.search_host(pinned[i % 2], out=pos_out)
+        counts.append(c)
+        kernel_s += mt.last_kernel_seconds
+    own_s = time.perf_counter() - t0
+    if world > 1:  # the counts of all steps cross NVLink in ONE all-reduce (8 B per step), not one blocking call per step
+        ct = torch.tensor(counts, dtype=torch.int64, device=dev)
+        dist.all_reduce(ct)
+        counts = [int(x) for x in ct.tolist()]
+    rig.barrier()
+    e2e_s, _ = rig.max_over_ranks(time.perf_counter() - t0)
     e2e_bytes = int(pinned[0].numel())
     e2e_value = world * e2e_bytes * e2e_steps / e2e_s / 1e9
-    sampler.stop_flag = True
-    sampler.join(timeout=1)
-    clocks = sampler.summary(t_wall0, t_wall1)
+    h2d = int(mt.last_h2d_bytes)
+    rep["e2e"] = {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "text_bytes_per_step": e2e_bytes,
+                  "h2d": ("hybrid: a prefix of the text copied one byte per symbol by DMA while the host cores pack the "
+                          "rest to 2 bits per symbol (csrc/hostpack.cpp)" if h2d < e2e_bytes
+                          else "text copied one byte per symbol"),
+                  "d2h_bytes_per_step": 8 * int(last_count) + 32, "steps": e2e_steps,
+                  "per_gpu_text_GBps_this_rank": e2e_bytes * e2e_steps / own_s / 1e9,
+                  "per_gpu_link_GBps_this_rank": h2d * e2e_steps / own_s / 1e9,
+                  "kernel_ms_per_step": kernel_s / e2e_steps * 1e3,
+                  "api": "acwm_search_host (pinned host text -> host count + positions)"}
 
     # ---- CPU baseline: the reference on the host cores (rank 0, N = 1 only)
-    cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         mt.scan_tensor(dev_texts[0], want_positions=False)
         gpu_count0, _, _ = mt.fetch(cap=0, stream=stream)
-        cpu = cpu_baseline(args, host_texts[0], pats, algo_name, alphabet, m, gpu_count0)
+        rep["cpu_baseline"] = cpu_baseline(host_texts[0], pats, algo_name, alphabet, m, gpu_count0)
+    mt.close()
+    return rep
+
+
+def run_ours(args):
+    rig = Rig(args)
+    torch, world, rank = rig.torch, rig.world, rig.rank
+    n = args.text_mib << 20  # per-GPU shard (weak scaling)
+    legs = args.workload.split("+")
+    per = {}
+    for wl in legs:
+        rep = run_leg(rig, wl, n, args.steps, args.warmup, full=True)
+        per[rep["algo"] if len(legs) > 1 else wl] = rep
+    link = measure_pinned_copy(torch, rig.dev)
+    _, links = rig.max_over_ranks(link)
+
+    # ---- the sizes the north star scales on: 1 GiB of DNA per GPU for both algorithms, configs[2] at 10^9 B per GPU
+    big = []
+    if not args.no_big_legs and args.workload == DEFAULT_WORKLOAD:
+        for wl, nb in (("c1", 1 << 30), ("c2", 1 << 30), ("c3", 10 ** 9)):
+            rep = run_leg(rig, wl, nb, max(5, args.steps // 5), 3, full=False)
+            big.append({k: rep[k] for k in ("workload", "algo", "text_bytes_per_gpu", "value", "unit", "ms_per_step",
+                                            "gpu_launches", "matches_last_step", "roofline", "kernel", "count_exchange",
+                                            "table_build_s")})
+    rig.sampler.stop_flag = True
+    rig.sampler.join(timeout=1)
+    clocks = rig.sampler.summary(rig.timed_windows[:len(legs)])
 
     if rank == 0:
-        info = mt.info
+        lim = pick_limiting(per)
+        e2e_lim = min(per, key=lambda k: per[k]["e2e"]["value"])
+        e2e = dict(per[e2e_lim]["e2e"])
+        e2e["leg"] = e2e_lim
+        e2e["pinned_copy_GBps_per_rank"] = [round(x, 2) for x in links]
+        e2e["affinity"] = rig.affinity
         line = {
-            "metric": "text GB/s scanned", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "algo": algo_name, "alphabet": alphabet,
-                       "patterns": p, "m": list(m) if isinstance(m, tuple) else m,
-                       "text_bytes_per_gpu": n, "halo_bytes": halo,
-                       "l2": (f"{N_ROTATE} distinct {args.text_mib} MiB texts cycled (working set > L2)" if N_ROTATE > 1
-                              else f"one {args.text_mib} MiB text per GPU (larger than L2)"),
-                       "positions": "count + sorted uint64 positions produced every step",
-                       "count_exchange": ("none (1 GPU)" if world == 1 else
-                                          "in-kernel st.release.sys into NVLink peer mailboxes (torch symmetric memory)"
-                                          if fused_exchange else "NCCL all_reduce of the 8-byte count per step"),
-                       "launch": "one kernel per step (scan + position ordering + result), no memset / finalize nodes; "
-                                 + ("cooperative launches" if args.no_overlap else
-                                    "consecutive steps chained as programmatic dependent launches (acwm_set_overlap)"),
-                       "kernel": {k: info[k] for k in ("packed2bit", "stride", "depth", "exact_front", "n_rows",
-                                                        "table_in_smem", "smem_bytes", "threads", "stages")}},
-            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(mt.last_h2d_bytes),
-                    "text_bytes_per_step": e2e_bytes,
-                    "h2d": ("hybrid: a prefix of the text copied one byte per symbol by DMA while the host cores pack the "
-                            "rest to 2 bits per symbol (csrc/hostpack.cpp)" if mt.last_h2d_bytes < e2e_bytes
-                            else "text copied one byte per symbol"),
-                    "d2h_bytes_per_step": 8 * int(e2e_count if world == 1 else last_count) + 32,
-                    "steps": e2e_steps, "api": "acwm_search_host (pinned host text -> host count + positions)"},
-            "gpu_launches": int(launches),
+            "metric": "text GB/s scanned", "value": per[lim]["value"], "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per[lim]["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args.workload, n),
+            "value_is": f"the slower leg ({lim}); every leg runs {args.steps} timed steps after {args.warmup} warm-up steps",
+            "per_algo": per,
+            "e2e": e2e,
+            "gpu_launches": int(sum(per[k]["gpu_launches"] for k in per)),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "scan_kernel (one launch: TMA-fed scan + barrier-free position ordering)",
-                         "kernel_ms": scan_mean * 1e3, "kernel_ms_isolated_launch": scan_isolated * 1e3,
-                         "duration_source": "timed region / K (one launch per step)" if scan_mean != scan_isolated
-                         else "CUDA events around single launches",
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "frac_of_8TBps_spec": achieved / 8000.0},
-            "matches_last_step": int(global_count),
-            "per_rank_ms_per_step": [round(x, 5) for x in per_rank_ms],
+            "roofline": per[lim]["roofline"],
+            "details": {
+                "l2": f"{N_ROTATE} distinct {args.text_mib} MiB texts cycled per leg (working set > L2)"
+                      if n <= (256 << 20) else f"one {args.text_mib} MiB text per GPU (larger than L2)",
+                "positions": "count + sorted uint64 positions produced every step",
+                "launch": "one kernel per step (scan + position ordering + result + count exchange), no memset / finalize "
+                          "nodes; " + ("cooperative launches" if args.no_overlap else
+                                       "consecutive steps chained as programmatic dependent launches (acwm_set_overlap)"),
+                "halo_bytes": {k: (WORKLOADS[per[k]["workload"]][3][1] if isinstance(WORKLOADS[per[k]["workload"]][3], tuple)
+                                   else WORKLOADS[per[k]["workload"]][3]) - 1 for k in per},
+            },
+            "matches_last_step": per[lim]["matches_last_step"],
+            "per_rank_ms_per_step": per[lim]["per_rank_ms_per_step"],
         }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+        if "cpu_baseline" in per[lim]:
+            line["cpu_baseline"] = per[lim]["cpu_baseline"]
+        if big:
+            line["north_star_legs"] = big
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        rig.dist.destroy_process_group()
 
 
 def _device_count_tensor(torch, ptr, dev):
@@ -395,23 +574,24 @@ def _device_count_tensor(torch, ptr, dev):
     return torch.as_tensor(w, device=dev)
 
 
-def cpu_baseline(args, text, pats, algo_name, alphabet, m, gpu_count):
+def cpu_baseline(text, pats, algo_name, alphabet, m, gpu_count):
     import oracle
     cores = os.cpu_count() or 1
     mixed = isinstance(m, tuple)
     n = text.size
-    use_ref = oracle.ref_available() and not mixed and not (algo_name == "AC" and len(pats) * pats.shape[1] > 400_000)
+    p = len(pats)
+    m_max = m[1] if mixed else m
+    use_ref = oracle.ref_available() and not mixed and not (algo_name == "AC" and p * m_max > 400_000)
     passes, tot, cnt = 0, 0.0, None
-    sample = text
     t_start = time.perf_counter()
     while passes < 5 and time.perf_counter() - t_start < 12.0:
         if use_ref:
-            r = (oracle.ref_ac if algo_name == "AC" else oracle.ref_wu)(pats, alphabet, sample, threads=cores)
+            r = (oracle.ref_ac if algo_name == "AC" else oracle.ref_wu)(pats, alphabet, text, threads=cores)
             tot += r["search_s"]
             cnt = r["count"]
         else:
             t0 = time.perf_counter()
-            cnt = oracle.set_search(pats, sample, want_positions=False)["count"]
+            cnt = oracle.set_search(pats, text, want_positions=False)["count"]
             tot += time.perf_counter() - t0
         passes += 1
     out = {"value": n * passes / tot / 1e9, "unit": "GB/s", "cores": cores if use_ref else 1,
@@ -431,13 +611,19 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD,
+                    help="c1+c2 (default: both algorithms, value = the slower) or any of " + ", ".join(sorted(WORKLOADS))
+                         + ", or several joined with +")
     ap.add_argument("--text-mib", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-big-legs", action="store_true", help="skip the 1 GiB / configs[2] legs of the default run")
     ap.add_argument("--no-overlap", action="store_true", help="plain cooperative launches in the timed loop")
     ap.add_argument("--matcher-opts", default="{}", help="JSON of acwm_options overrides (tuning experiments)")
     ap.add_argument("--nccl-count", action="store_true", help="all-reduce the count with NCCL instead of in-kernel")
     args = ap.parse_args()
+    for wl in args.workload.split("+"):
+        if wl not in WORKLOADS:
+            ap.error(f"unknown workload {wl}")
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)

@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libacwm_b200.so")
 AC, WM = 0, 1
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_OVERFLOW, ERR_BAD_TEXT = range(7)
 
-BLOB_FRONT, BLOB_FILTER2, BLOB_BUCKET_START, BLOB_ENTRIES, BLOB_PATTERNS, BLOB_PARAMS, BLOB_SYMCLASS, BLOB_RMASK = range(8)
+BLOB_FRONT, BLOB_FILTER2, BLOB_BUCKET_START, BLOB_ENTRIES, BLOB_PATTERNS, BLOB_PARAMS, BLOB_SYMCLASS, BLOB_RMASK, BLOB_VDFA = range(9)
 
 
 class AcwmError(RuntimeError):
@@ -39,14 +39,15 @@ class Options(C.Structure):
     _fields_ = [("smem_table_budget", C.c_uint32), ("force_stride", C.c_uint32), ("force_depth", C.c_uint32),
                 ("force_bytes_path", C.c_uint32), ("force_threads", C.c_uint32), ("force_stages", C.c_uint32),
                 ("force_f2_bits", C.c_uint32), ("force_r_bits", C.c_uint32), ("force_smem_tables", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("force_front", C.c_uint32), ("force_ctas", C.c_uint32)]
 
 
 class Info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in
                 ("algo", "alphabet", "n_patterns", "n_distinct", "m_min", "m_max", "packed2bit", "stride", "depth",
                  "exact_front", "n_states", "n_rows", "table_in_smem", "smem_bytes")] + \
-               [("table_bytes", C.c_uint64), ("threads", C.c_uint32), ("stages", C.c_uint32)]
+               [("table_bytes", C.c_uint64), ("threads", C.c_uint32), ("stages", C.c_uint32), ("ctas_per_sm", C.c_uint32),
+                ("front_kind", C.c_uint32)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
@@ -56,8 +57,7 @@ class ScanParams(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in
                 ("algo", "packed2bit", "alphabet", "m_min", "m_max", "stride", "depth", "exact_front", "n_rows",
                  "f1_sh1", "f1_mult", "f1_sh2", "f1_words", "b2", "f2_mult", "f2_sh", "f2_words", "hb_mult",
-                 "hb_sh", "n_buckets", "n_entries", "n_classes", "r_mult", "r_sh", "r_entries", "r_entry_bytes", "r_in_smem", "f2_in_smem")] + \
-               [("reserved", C.c_uint32 * 2)]
+                 "hb_sh", "n_buckets", "n_entries", "n_classes", "r_mult", "r_sh", "r_entries", "r_entry_bytes", "r_in_smem", "f2_in_smem", "front_kind", "verify_kind", "v_rows", "ilp")]
 
 
 VENTRY_DTYPE = np.dtype([("key", "<u4"), ("len", "<u4"), ("offset", "<u8")])

@@ -66,7 +66,7 @@ static int ensure_positions(acwm_matcher *mt, uint64_t cap) {
 	// staging: one reservation block of slack per warp the widest grid can hold
 	// a warp's reservations double in size: at most as many slots idle as it fills, plus its first block
 	mt->stage_cap = 2 * cap + (uint64_t) 2 * kStageBlock * 32 * (uint64_t) std::max(mt->sm_count, 1);
-	CU(cudaMalloc((void **) &mt->d_staging, 2 * mt->stage_cap * 8)); // two copies, by launch parity (see Work)
+	CU(cudaMalloc((void **) &mt->d_staging, kScratchRing * mt->stage_cap * 8)); // one copy per scan in flight (see Work)
 	CU(cudaMalloc((void **) &mt->d_positions, cap * 8));
 	mt->pos_cap = cap;
 	return ACWM_OK;
@@ -80,7 +80,7 @@ static int ensure_tiles(acwm_matcher *mt, uint64_t n_tiles) {
 	mt->d_tile_count = nullptr;
 	mt->tile_cap = 0;
 	const uint64_t want = n_tiles + n_tiles / 8 + 1024;
-	CU(cudaMalloc((void **) &mt->d_tile_count, 2 * want * 4)); // two copies, by launch parity
+	CU(cudaMalloc((void **) &mt->d_tile_count, kScratchRing * want * 4)); // one copy per scan in flight
 	mt->tile_cap = want;
 	return ACWM_OK;
 }
@@ -102,21 +102,25 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	const struct {
 		const void *src;
 		size_t bytes;
-	} parts[6] = {{c.front.data(), c.front.size()}, {c.rmask.data(), c.rmask.size()},
+	} parts[7] = {{c.front.data(), c.front.size()}, {c.rmask.data(), c.rmask.size()},
 			{c.filter2.data(), c.filter2.size() * 4}, {c.bucket_start.data(), c.bucket_start.size() * 4},
-			{c.entries.data(), c.entries.size() * sizeof(acwm_ventry)}, {mt->ps.bytes.data(), mt->ps.bytes.size()}};
-	size_t off[6], total = 0;
-	for (int i = 0; i < 6; i++) {
+			{c.entries.data(), c.entries.size() * sizeof(acwm_ventry)}, {mt->ps.bytes.data(), mt->ps.bytes.size()},
+			{c.vdfa.data(), c.vdfa.size() * 4}};
+	size_t off[7], total = 0;
+	for (int i = 0; i < 7; i++) {
 		off[i] = total;
 		total += (std::max<size_t>(parts[i].bytes, 16) + 255) & ~(size_t) 255;
 	}
 	if ((rc = dev_upload(&mt->d_tables, nullptr, total)))
 		return rc;
 	CU(cudaMemset(mt->d_tables, 0, total));
-	for (int i = 0; i < 6; i++)
+	for (int i = 0; i < 7; i++)
 		if (parts[i].bytes)
 			CU(cudaMemcpy(mt->d_tables + off[i], parts[i].src, parts[i].bytes, cudaMemcpyHostToDevice));
-	mt->tables_bytes = total;
+	// the access-policy window covers what every tile reads; the verify DFA (last part) is touched by the rare
+	// candidate windows only and stays outside
+	mt->tables_bytes = off[6];
+	mt->d_vdfa = reinterpret_cast<uint32_t *>(mt->d_tables + off[6]);
 	mt->d_front = mt->d_tables + off[0];
 	mt->d_rmask = mt->d_tables + off[1];
 	mt->d_filter2 = reinterpret_cast<uint32_t *>(mt->d_tables + off[2]);
@@ -127,9 +131,9 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	CU(cudaMemset(mt->d_ctl, 0, sizeof(Control)));
 	CU(cudaMallocHost((void **) &mt->h_res, sizeof(Result)));
 	CU(cudaMallocHost((void **) &mt->h_bounce, kBounceEntries * 8));
-	CU(cudaMalloc((void **) &mt->d_cta_total, 2 * kMaxScanBlocks * sizeof(unsigned long long)));
+	CU(cudaMalloc((void **) &mt->d_cta_total, kScratchRing * kMaxScanBlocks * sizeof(unsigned long long)));
 	// the span totals are recognised by their launch tag: recycled device memory must not hold a look-alike
-	CU(cudaMemset(mt->d_cta_total, 0, 2 * kMaxScanBlocks * sizeof(unsigned long long)));
+	CU(cudaMemset(mt->d_cta_total, 0, kScratchRing * kMaxScanBlocks * sizeof(unsigned long long)));
 	CU(cudaStreamCreateWithFlags(&mt->s_copy, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&mt->s_scan, cudaStreamNonBlocking));
 	for (auto &e : mt->ev_copy)
@@ -194,9 +198,10 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.bucket_start = mt->d_bucket_start;
 	a.entries = mt->d_entries;
 	a.patterns = mt->d_patterns;
+	a.vdfa = mt->d_vdfa;
 	a.prm = c.prm;
 	a.ctl = mt->d_ctl;
-	const uint32_t par = mt->epoch & 1u; // the scratch arrays of this launch (its predecessor may still be reading the others)
+	const uint32_t par = mt->epoch % kScratchRing; // the scratch arrays of this launch (its two predecessors may still be using theirs)
 	a.staging = mt->d_staging ? mt->d_staging + par * mt->stage_cap : nullptr;
 	a.positions = mt->d_positions;
 	a.cap = want_positions ? mt->pos_cap : 0;
@@ -219,18 +224,28 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	}
 	const uint32_t threads = c.info.threads, warps = threads / 32;
 	const uint64_t ntl = tile_hi - tile_lo;
+	const bool dual = c.info.ctas_per_sm == 2;
+	const uint32_t sms = (uint32_t) std::max(mt->sm_count, 1);
+	// Overlap mode (device-resident scans only; exchange == "called from acwm_scan_device"): one CTA per SM, launched
+	// as a programmatic dependent launch, so that the CTAs of consecutive scans share the SMs (two half-size CTAs of
+	// two scans per SM) or follow each other on them without a grid-wide gap (one full-size CTA per SM).  What keeps
+	// at most three scans in flight (see Work in scan_common.cuh): the grid fills every SM and an SM holds at most
+	// two CTAs of this kernel -- dual CTAs take more than a third of its shared memory, single ones more than half.
+	const bool chain = exchange && mt->overlap && ntl >= (uint64_t) sms * warps;
 	// every CTA owns a contiguous span of whole "rounds" (one tile per warp)
-	uint32_t grid = (uint32_t) std::min<uint64_t>((uint64_t) std::min(mt->sm_count, 256), (ntl + warps - 1) / warps);
+	const uint32_t max_grid = std::min<uint32_t>(chain ? sms : sms * (dual ? 2u : 1u), kMaxScanBlocks);
+	uint32_t grid = (uint32_t) std::min<uint64_t>(max_grid, (ntl + warps - 1) / warps);
 	grid = std::max(grid, 1u);
 	a.tiles_per_cta = std::max<uint64_t>(1, (ntl + grid - 1) / grid);
 	grid = (uint32_t) std::max<uint64_t>(1, (ntl + a.tiles_per_cta - 1) / a.tiles_per_cta);
 	// per-tile counts of a span stay in whatever shared memory the tables and the rings leave free
-	a.cnt_cap = (uint32_t) std::min<uint64_t>(a.tiles_per_cta, (kMaxSmem - c.info.smem_bytes) / 4);
+	const uint32_t smem_max = dual ? kMaxSmemDual : kMaxSmem;
+	a.cnt_cap = (uint32_t) std::min<uint64_t>(a.tiles_per_cta, (smem_max - c.info.smem_bytes) / 4);
 	const uint32_t smem = c.info.smem_bytes + a.cnt_cap * 4;
-	// overlap mode (device-resident scans only; exchange == "called from acwm_scan_device"): a programmatic
-	// dependent launch, for grids that fill the GPU with CTAs that own their SM -- what keeps at most two
-	// consecutive scans in flight (see Work in scan_common.cuh)
-	a.pdl = (exchange && mt->overlap && grid == (uint32_t) mt->sm_count && 2 * (smem + 1024) > kMaxSmem + 1024) ? 1 : 0;
+	const bool two_at_most = 3 * (smem + 1024) > kSmemPerSmTotal; // CTAs of this kernel per SM
+	a.pdl = (chain && grid == sms && two_at_most) ? 1 : 0;
+	if (grid > 256)
+		a.trace = nullptr; // the trace buffer holds 256 CTAs
 	cudaError_t e = c.prm.packed2bit ? launch_scan_packed(a, threads, smem, grid, st)
 									 : launch_scan_bytes(a, threads, smem, grid, st);
 	if (e != cudaSuccess)
@@ -963,6 +978,7 @@ int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_
 	case ACWM_BLOB_PARAMS: *ptr = &c.prm; *bytes = sizeof(c.prm); break;
 	case ACWM_BLOB_SYMCLASS: *ptr = c.symclass.data(); *bytes = c.symclass.size(); break;
 	case ACWM_BLOB_RMASK: *ptr = c.rmask.data(); *bytes = c.rmask.size(); break;
+	case ACWM_BLOB_VDFA: *ptr = c.vdfa.data(); *bytes = c.vdfa.size() * 4; break;
 	default: return set_error(ACWM_ERR_INVALID, "unknown blob id");
 	}
 	return ACWM_OK;

@@ -24,43 +24,60 @@ constexpr uint32_t kListCap = 128;                  // per-warp list of match po
 constexpr uint32_t kLogCap = 24;                    // per-warp log of its staging reservations (they double in size)
 constexpr uint32_t kMaxGrabLog2 = 23;               // largest single reservation: 2^23 slots
 
-// per-warp shared memory: ring of raw tiles, (2-bit path) 2-bit copy of the current tile for the
-// verification windows, one mbarrier + one tile id per ring slot, match list, reservation log
-constexpr uint32_t warp_smem_bytes(uint32_t stages, bool packed) {
-	return stages * kBufBytes + (packed ? kPackWords * 4 : 0) + kMaxStages * 16 + kListCap * 2 + kLogCap * 8;
+// per-warp shared memory: ring of raw tiles, (2-bit path with a verification stage) 2-bit copy of the current tile
+// for the verification windows, one mbarrier + one tile id per ring slot, match list, reservation log
+constexpr uint32_t warp_smem_bytes(uint32_t stages, bool pk_copy) {
+	return stages * kBufBytes + (pk_copy ? kPackWords * 4 : 0) + kMaxStages * 16 + kListCap * 2 + kLogCap * 8;
 }
 
 constexpr uint32_t kMaxSmem = 227 * 1024;
 constexpr uint32_t kSmemReserve = 1024;             // CTA-level scratch (barriers, finalize scan), alignment slack
+// Two CTAs per SM (the shape overlap mode prefers: consecutive scans share every SM, one scans while the other is in
+// its prologue or its ordering epilogue): 228 KiB per SM, 1 KiB of it reserved per resident CTA.  A dual CTA asks for
+// MORE than a third of the SM so that never three are resident (the in-flight bound behind the Work ring).
+constexpr uint32_t kSmemPerSmTotal = 228 * 1024;
+constexpr uint32_t kMaxSmemDual = kSmemPerSmTotal / 2 - 1024;
+constexpr uint32_t kMinSmemDual = kSmemPerSmTotal / 3 - 1024 + 256;
 
 // Staging entry: [tile:28 | rank:22 | pos_in_tile:14]
 constexpr uint32_t kPosBits = 14, kRankBits = 22;
 constexpr uint32_t kStageBlockLog2 = 7;
 constexpr uint32_t kStageBlock = 1u << kStageBlockLog2; // staging slots of a warp's first reservation (each further one doubles)
 
-// (warps, stages) the scan kernel is launched with, in order of preference.  The 2-bit path
+// (warps, stages, CTAs per SM) the scan kernel is launched with, in order of preference.  The 2-bit path
 // copies a tile into registers first and refills its slot while it walks, so one slot per
 // warp already overlaps load and scan; the bytes path reads the raw tile throughout.
 struct LaunchShape {
-	uint32_t warps, stages;
+	uint32_t warps, stages, ctas;
 };
-constexpr LaunchShape kShapesPacked[] = {{32, 1}, {24, 1}, {16, 2}, {16, 1}, {12, 2}, {12, 1}, {8, 2}, {8, 1}, {4, 2}, {4, 1}};
-constexpr LaunchShape kShapesBytes[] = {{16, 2}, {12, 2}, {8, 2}, {4, 2}};
+constexpr LaunchShape kShapesPacked[] = {{32, 1, 1}, {24, 1, 1}, {16, 2, 1}, {16, 1, 1}, {12, 2, 1}, {12, 1, 1}, {8, 2, 1}, {8, 1, 1}, {4, 2, 1}, {4, 1, 1}};
+constexpr LaunchShape kShapesPackedDual[] = {{16, 1, 2}, {12, 1, 2}};
+constexpr LaunchShape kShapesBytes[] = {{16, 2, 1}, {12, 2, 1}, {8, 2, 1}, {4, 2, 1}};
 
-inline bool shape_fits(uint32_t table_bytes, LaunchShape s, bool packed) {
-	return table_bytes + s.warps * warp_smem_bytes(s.stages, packed) + kSmemReserve <= kMaxSmem;
+inline uint32_t shape_smem(uint32_t table_bytes, LaunchShape s, bool pk_copy) {
+	return table_bytes + s.warps * warp_smem_bytes(s.stages, pk_copy) + kSmemReserve;
 }
-inline LaunchShape shape_for_tables(uint32_t table_bytes, bool packed) {
+inline bool shape_fits(uint32_t table_bytes, LaunchShape s, bool pk_copy) {
+	return shape_smem(table_bytes, s, pk_copy) <= (s.ctas == 2 ? kMaxSmemDual : kMaxSmem);
+}
+// packed: the 2-bit path; pk_copy: its kernels keep a 2-bit copy of the tile (everything but the exact automaton)
+inline LaunchShape shape_for_tables(uint32_t table_bytes, bool packed, bool pk_copy, bool dual = false) {
+	if (packed && dual) {
+		for (const LaunchShape &s : kShapesPackedDual)
+			if (shape_fits(table_bytes, s, pk_copy))
+				return s;
+		return LaunchShape{0, 0, 0};
+	}
 	if (packed) {
 		for (const LaunchShape &s : kShapesPacked)
-			if (shape_fits(table_bytes, s, true))
+			if (shape_fits(table_bytes, s, pk_copy))
 				return s;
 	} else {
 		for (const LaunchShape &s : kShapesBytes)
 			if (shape_fits(table_bytes, s, false))
 				return s;
 	}
-	return LaunchShape{0, 0};
+	return LaunchShape{0, 0, 0};
 }
 
 } // namespace acwm

@@ -11,6 +11,9 @@
 #include <cstring>
 #include <ctime>
 
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -83,11 +86,18 @@ constexpr uint64_t kPiece = HostPacker::kPieceSymbols; // symbols per work item 
 HostPacker::HostPacker(unsigned threads) {
 	fn_ = (void *) pick_pack();
 	if (threads == 0) {
-		threads = std::thread::hardware_concurrency();
-		if (threads == 0)
-			threads = 4;
-		// one process per GPU (torchrun): the ranks of a box share its cores
-		if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+		const unsigned hw = std::thread::hardware_concurrency();
+		threads = hw ? hw : 4;
+		unsigned allowed = 0;
+#if defined(__linux__)
+		cpu_set_t set;
+		if (sched_getaffinity(0, sizeof(set), &set) == 0)
+			allowed = (unsigned) CPU_COUNT(&set);
+#endif
+		if (allowed && allowed < threads)
+			threads = allowed; // the launcher gave this process its own cores (bench.py pins every rank to a slice)
+		else if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+			// one process per GPU (torchrun), all on the same cores: the ranks of a box share them
 			const unsigned w = (unsigned) strtoul(e, nullptr, 10);
 			if (w > 1)
 				threads = threads / w ? threads / w : 1;

@@ -37,6 +37,7 @@ struct acwm_matcher {
 	uint32_t *d_bucket_start = nullptr;
 	acwm_ventry *d_entries = nullptr;
 	uint8_t *d_patterns = nullptr;
+	uint32_t *d_vdfa = nullptr;
 	acwm::Control *d_ctl = nullptr;
 	acwm::Result *h_res = nullptr;
 	uint64_t *h_bounce = nullptr; // pinned: the first positions of a result

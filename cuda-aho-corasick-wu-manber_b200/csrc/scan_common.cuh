@@ -19,13 +19,15 @@ struct Result {
 	unsigned int order_failed;   // launch number + 1 of the last scan whose position ordering gave up (never in practice)
 };
 
-// Working counters of the launch in flight.  Three copies: launch k uses work[k % 3] and clears
-// work[(k + 1) % 3] when it STARTS (before it lets its successor in).  In overlap mode two
-// consecutive launches run at the same time (never three: a full grid of one-per-SM CTAs only finds room
-// as its predecessor's CTAs exit, and those exit only after THEIR predecessor has completed), so the copy
-// being cleared belongs to a launch that is over and the successor finds its copy zeroed.  No memset node
+// Working counters of the launch in flight.  kWorkRing copies: launch k uses work[k % 4] and clears
+// work[(k + 1) % 4] when it STARTS (before it lets its successor in).  In overlap mode consecutive launches run
+// at the same time, at most THREE of them: every launch of the chain puts one CTA on every SM (grid = #SMs) and
+// an SM holds at most two CTAs of this kernel (shared memory: a CTA takes more than a third of the SM), so CTAs
+// of launch k + 2 find room only as CTAs of launch k exit -- and those exit only after launch k - 1 has
+// completed (griddepcontrol.wait before the arrival).  Hence when launch k starts and clears the copy of launch
+// k + 1 = the copy of launch k - 3, that launch is over, and the successor finds its copy zeroed.  No memset node
 // between scans.  The scratch arrays the scan phase writes (staging, per-tile counts, per-CTA totals)
-// exist twice, selected by launch parity, for the same reason.
+// exist kScratchRing = 3 times, selected by launch number, for the same reason.
 struct Work {
 	unsigned long long arrive;   // [CTAs arrived : 16 | matches : 48] -- one atomic per CTA is count, grid barrier, exit
 	                             // ticket and (by arrival order) the CTA's role in the ordering epilogue
@@ -44,9 +46,11 @@ constexpr unsigned long long kLookbackTimeoutNs = 2000ull * 1000 * 1000; // a pr
 // ScanArgs.tune bits
 constexpr uint32_t kTuneCoopVerify = 1u;
 
+constexpr uint32_t kWorkRing = 4, kScratchRing = 3;
+
 struct Control {
 	Result result;
-	Work work[3];
+	Work work[kWorkRing];
 };
 
 struct ScanArgs {
@@ -63,6 +67,7 @@ struct ScanArgs {
 	const uint32_t *bucket_start;
 	const acwm_ventry *entries;
 	const uint8_t *patterns;
+	const uint32_t *vdfa;        // filtered AC: the automaton that decides a candidate window (global memory)
 	acwm_scan_params prm;
 	Control *ctl;
 	uint64_t *staging;           // [tile:28 | rank:22 | pos:14]
@@ -264,8 +269,27 @@ struct Emitter {
 // the bucket `key` hashes to (the HASH -> PREFIX -> compare tail of Wu-Manber,
 // wu/wu.c:81-99, also used for the hits of a depth-truncated AC automaton).
 // Returns how many distinct patterns end at e.
+// Filtered AC (front_kind 1): the window of m symbols ending at virtual position e is walked through the full-depth
+// automaton from its root (one symbol per lookup, ac/ac.c:207-219 with the failure function folded in); the walk ends
+// on a final state iff the window is a pattern.  Reached by the few windows the block filter and the stage-2
+// bitmap let through, i.e. hardly more often than there are matches.
+static __device__ __noinline__ uint32_t verify_dfa(const ScanArgs &a, uint64_t e) {
+	const uint32_t m = a.prm.m_min;
+	if (e + 1 < a.data_lo + m || e >= a.data_hi || e < a.report_lo)
+		return 0; // window would start before the text / end after it / not ours to report
+	const uint64_t s0 = e + 1 - m;
+	uint32_t ent = 0;
+	for (uint32_t k = 0; k < m; k++) {
+		const uint32_t sym = a.packed_in ? ((a.text16[(s0 + k) >> 2] >> (2 * ((s0 + k) & 3))) & 3u) : (a.text16[s0 + k] & 3u);
+		ent = __ldg(a.vdfa + ((ent >> 1) << 2) + sym);
+	}
+	return ent & 1u;
+}
+
 __device__ __forceinline__ uint32_t verify_window(const ScanArgs &a, uint32_t key, uint64_t e) {
 	const acwm_scan_params &p = a.prm;
+	if (p.verify_kind)
+		return verify_dfa(a, e);
 	const uint32_t b = (uint32_t) (key * p.hb_mult) >> p.hb_sh;
 	const uint32_t lo = __ldg(a.bucket_start + b), hi = __ldg(a.bucket_start + b + 1);
 	uint32_t mult = 0;

@@ -13,18 +13,21 @@
 //               publishes the span total as a tagged word and looks back over the totals of the spans
 //               in front of it; then every warp moves its own staged matches to their sorted slots;
 //   3. publish  a CTA's arrival is ONE 64-bit atomic that also carries its match count; the last
-//               CTA to arrive writes the result block.  The working counters exist three times
-//               (launch k uses copy k % 3 and zeroes copy k + 1 as it starts), the scratch arrays twice
-//               (by launch parity): no memset node between scans.
-// Overlap mode (acwm_set_overlap): the launch is a programmatic dependent launch -- CTAs of scan k + 1 take
-// over SMs as CTAs of scan k retire and run their whole scan phase on their own copies of the scratch state;
-// thread 0 waits for scan k (griddepcontrol.wait) only before the arrival.  At most two scans are in flight
-// (see Work in scan_common.cuh).
+//               CTA to arrive writes the result block.  The working counters exist four times
+//               (launch k uses copy k % 4 and zeroes copy k + 1 as it starts), the scratch arrays three
+//               times (by launch number): no memset node between scans.
+// Overlap mode (acwm_set_overlap): the launch is a programmatic dependent launch -- CTAs of scan k + 1 become
+// resident beside (two half-size CTAs per SM) or right after (one CTA per SM) the CTAs of scan k and run their
+// whole scan phase on their own copies of the scratch state; thread 0 waits for scan k (griddepcontrol.wait)
+// only before the arrival.  With two CTAs per SM every SM always has one CTA scanning while the other is in its
+// prologue or its ordering epilogue.  At most three scans are in flight (see Work in scan_common.cuh).
 //   4. exchange (multi-GPU) the publishing thread stores the rank's count into every peer's mailbox
 //               over NVLink (system-scope stores on peer-mapped memory) and, at its very end, sums
 //               what the peers left in its own mailbox for the PREVIOUS scan: an all-reduce of the
 //               8-byte count, pipelined by one scan, without another launch or a lock-step wait.
 #pragma once
+#include <atomic>
+
 #include "scan_common.cuh"
 
 namespace acwm {
@@ -76,11 +79,12 @@ __device__ __forceinline__ bool tile_is_interior(const ScanArgs &a, uint64_t til
 	return tile >= 1 && (tile + 1) * (uint64_t) kTile <= (a.data_hi & ~(uint64_t) 15);
 }
 
-template <class Front, bool EXACT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant__ ScanArgs a) {
+template <class Front, bool EXACT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_constant__ ScanArgs a) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	constexpr uint32_t W = THREADS / 32;
 	constexpr bool kPacked = Front::kPacked;
+	constexpr bool kPk = kPacked && !EXACT; // the 2-bit copy of the tile exists for the verification windows only
 	// [CTA scratch 1 KiB][front table][offset masks][stage-2 bitmap][per-warp areas]
 	uint64_t *tab_bar = reinterpret_cast<uint64_t *>(smem);
 	uint32_t *s_next = reinterpret_cast<uint32_t *>(smem + 16); // next unclaimed tile of this CTA's span
@@ -99,14 +103,14 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 
 	const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
 	const uint32_t stages = a.stages;
-	uint8_t *wbase = s_warps + warp * warp_smem_bytes(stages, kPacked);
+	uint8_t *wbase = s_warps + warp * warp_smem_bytes(stages, kPk);
 	uint8_t *bufs = wbase;
 	uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + stages * kBufBytes);
-	uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + stages * kBufBytes + (kPacked ? kPackWords * 4 : 0));
+	uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + stages * kBufBytes + (kPk ? kPackWords * 4 : 0));
 	uint32_t *s_tid = reinterpret_cast<uint32_t *>(bars + kMaxStages); // span-relative tile index per ring slot
 	uint16_t *lst = reinterpret_cast<uint16_t *>(bars + 2 * kMaxStages);  // match positions of the current tile
 	unsigned long long *wlog = reinterpret_cast<unsigned long long *>(lst + kListCap); // this warp's staging reservations
-	uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_warps + W * warp_smem_bytes(stages, kPacked)); // a.cnt_cap words
+	uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_warps + W * warp_smem_bytes(stages, kPk)); // a.cnt_cap words
 
 	// this CTA's span of warp tiles; the warps claim its tiles one at a time (shared-memory ticket)
 	const uint64_t cta_lo = min(a.tile_lo + (uint64_t) blockIdx.x * a.tiles_per_cta, a.tile_hi);
@@ -118,6 +122,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	// warp, W + warp, ..); the CTA meets only afterwards, under the copies
 	if (threadIdx.x == 0) {
 		trace_mark(a, 0);
+		if (a.trace) { // which SM this CTA runs on (word 11): who shares an SM with whom in overlap mode
+			uint32_t smid;
+			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+			a.trace[(size_t) blockIdx.x * kTraceWords + 11] = smid;
+		}
 		mbar_init(tab_bar, 1);
 		*s_next = stages * W;
 		*s_bad = 0;
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	if (lane < 4)
 		for (uint32_t s = 0; s < stages; s++) // pad behind each buffer: read, never used
 			reinterpret_cast<uint32_t *>(bufs + s * kBufBytes + kLoadBytes)[lane] = 0;
-	if (kPacked && lane < 3)
+	if (kPk && lane < 3)
 		pk[kPackWords - 3 + lane] = 0;
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncwarp();
@@ -198,7 +207,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	if (blockIdx.x == 0 && threadIdx.x == THREADS - 1) {
 		// the successor's counters (see Work): zero in L2 before the successor may start (it may once every CTA
 		// of ours has passed the trigger below); done by a lane that has nothing to issue, under the first copies
-		Work *nxt = &a.ctl->work[(a.epoch + 1u) % 3u];
+		Work *nxt = &a.ctl->work[(a.epoch + 1u) % kWorkRing];
 		__stcg(&nxt->arrive, 0ull);
 		__stcg(&nxt->cursor, 0ull);
 		__stcg(&nxt->bad_text, 0u);
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 	}
 
 	uint32_t badacc = 0;
-	Work *wk = &a.ctl->work[a.epoch % 3u];
+	Work *wk = &a.ctl->work[a.epoch % kWorkRing];
 	Emitter em;
 	em.a = &a;
 	em.wk = wk;
@@ -634,20 +643,20 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------ launch helper
-template <class Front, bool EXACT, int THREADS>
+template <class Front, bool EXACT, int THREADS, int MINB>
 static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid, cudaStream_t st) {
-	auto kern = scan_kernel<Front, EXACT, THREADS>;
-	static bool attr_set[64] = {};
+	auto kern = scan_kernel<Front, EXACT, THREADS, MINB>;
+	static std::atomic<bool> attr_set[64]; // per device; shard threads of one process launch concurrently
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess)
 		return e;
-	if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+	if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
 		e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxSmem);
 		if (e != cudaSuccess)
 			return e;
 		if (dev >= 0 && dev < 64)
-			attr_set[dev] = true;
+			attr_set[dev].store(true, std::memory_order_release);
 	}
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof(cfg));
@@ -655,10 +664,10 @@ static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid,
 	cfg.blockDim = dim3(THREADS);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = st;
-	// One CTA per SM (grid <= #SMs).  Plain scans are launched cooperatively (the runtime checks that the grid
-	// is resident at once: the span look-back then never waits for a CTA that has not started); overlap mode
-	// trades that for a programmatic dependent launch -- used only for grids of SM-filling CTAs, which all find
-	// an SM as the previous scan's CTAs retire (the two attributes together serialise, profiles/README.md session i).
+	// Plain scans are launched cooperatively (the runtime checks that the grid is resident at once: the span
+	// look-back then never waits for a CTA that has not started); overlap mode trades that for a programmatic
+	// dependent launch -- used only for grids of one CTA per SM, whose CTAs all find room as the CTAs of the scan
+	// two launches back retire (the two attributes together serialise, profiles/README.md session i).
 	cudaLaunchAttribute attr[1];
 	if (a.pdl) {
 		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -672,20 +681,28 @@ static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid,
 	return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
+// 2-bit path: 1024 / 768 threads own their SM; 512 / 384 threads are compiled for two CTAs per SM (64 / 80
+// registers) and serve both shapes.  The bytes path needs two raw slots per warp: at most 16 warps fit.
 template <class Front, bool EXACT>
 static cudaError_t launch_front(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st) {
-	if constexpr (Front::kPacked) { // the bytes path needs two raw slots per warp: at most 16 warps fit
-		if (threads == 1024)
-			return launch_shape<Front, EXACT, 1024>(a, smem, grid, st);
-		if (threads == 768)
-			return launch_shape<Front, EXACT, 768>(a, smem, grid, st);
-	}
-	switch (threads) {
-	case 512: return launch_shape<Front, EXACT, 512>(a, smem, grid, st);
-	case 384: return launch_shape<Front, EXACT, 384>(a, smem, grid, st);
-	case 256: return launch_shape<Front, EXACT, 256>(a, smem, grid, st);
-	case 128: return launch_shape<Front, EXACT, 128>(a, smem, grid, st);
-	default: return cudaErrorInvalidValue;
+	if constexpr (Front::kPacked) {
+		switch (threads) {
+		case 1024: return launch_shape<Front, EXACT, 1024, 1>(a, smem, grid, st);
+		case 768: return launch_shape<Front, EXACT, 768, 1>(a, smem, grid, st);
+		case 512: return launch_shape<Front, EXACT, 512, 2>(a, smem, grid, st);
+		case 384: return launch_shape<Front, EXACT, 384, 2>(a, smem, grid, st);
+		case 256: return launch_shape<Front, EXACT, 256, 2>(a, smem, grid, st);
+		case 128: return launch_shape<Front, EXACT, 128, 2>(a, smem, grid, st);
+		default: return cudaErrorInvalidValue;
+		}
+	} else {
+		switch (threads) {
+		case 512: return launch_shape<Front, EXACT, 512, 1>(a, smem, grid, st);
+		case 384: return launch_shape<Front, EXACT, 384, 1>(a, smem, grid, st);
+		case 256: return launch_shape<Front, EXACT, 256, 1>(a, smem, grid, st);
+		case 128: return launch_shape<Front, EXACT, 128, 1>(a, smem, grid, st);
+		default: return cudaErrorInvalidValue;
+		}
 	}
 }
 

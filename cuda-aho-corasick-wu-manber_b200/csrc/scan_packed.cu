@@ -78,7 +78,11 @@ struct PackedKey {
 // start kOff symbols in front of the chunk (kOff = 2 for K = 3, since 112 = 3*37 + 1),
 // preceded by the warm-up strides that bring the state up to date.
 // GLOBAL: the automaton lives in global memory (L2-resident), uint32 entries, K <= 2.
-template <int K, bool EXACT, bool GLOBAL = false>
+// ILP = 2: the lane walks its chunk as TWO independent chains (first and second half of the strides, the second
+// with its own warm-up over the symbols in front of it: prm.depth - 1 <= 30 of them).  A walk is a chain of
+// dependent shared-memory lookups, ~35 cycles each; two chains per lane keep twice as many lookups in flight per
+// warp, which is what a CTA of 12-16 warps (two CTAs per SM) needs to keep the shared-memory pipe busy.
+template <int K, bool EXACT, bool GLOBAL = false, int ILP = 1>
 struct FrontAC : PackedKey {
 	static constexpr int kSS = GLOBAL ? 2 : 1;                  // log2(entry bytes): symbols sit above it in the address
 	static constexpr int kOff = (K - (int) kLane % K) % K;      // 2 / 0 / 0
@@ -94,6 +98,7 @@ struct FrontAC : PackedKey {
 	const uint8_t *tab; // shared-memory DFA
 	uint32_t ent;       // current entry (byte offset of the row | hits)
 	uint32_t nwu, hist; // warm-up strides / symbols of history they (and the first in-chunk stride) cover
+	uint32_t a_depth;
 	uint32_t W[8];      // W[0] = the 16 symbols in front of the chunk, W[1..7] = the chunk
 	uint32_t H[3];      // long warm-up only: symbols -64..-17
 	uint32_t hw[kWords];
@@ -103,6 +108,7 @@ struct FrontAC : PackedKey {
 		// the state must have seen depth-1 symbols of history when the chunk starts; the first
 		// in-chunk stride covers kOff of them
 		const uint32_t need = a.prm.depth - 1;
+		a_depth = a.prm.depth;
 		nwu = need > (uint32_t) kOff ? (need - kOff + K - 1) / K : 0u;
 		hist = kOff + K * nwu; // <= 16: W[0] is enough; else up to 64 symbols of raw history
 	}
@@ -111,13 +117,47 @@ struct FrontAC : PackedKey {
 		return 1u; // a hit of the truncated automaton is probed where it ends
 	}
 
-	__device__ __forceinline__ uint32_t step(uint32_t sym2) {
-		const uint32_t addr = (ent & kRowMask) | sym2; // one LOP3 between two dependent lookups
+	__device__ __forceinline__ uint32_t step_of(uint32_t &e, uint32_t sym2) const {
+		const uint32_t addr = (e & kRowMask) | sym2; // one LOP3 between two dependent lookups
 		if (GLOBAL)
-			ent = __ldg(reinterpret_cast<const uint32_t *>(tab + addr));
+			e = __ldg(reinterpret_cast<const uint32_t *>(tab + addr));
 		else
-			ent = *reinterpret_cast<const uint16_t *>(tab + addr);
-		return ent & kHitMask;
+			e = *reinterpret_cast<const uint16_t *>(tab + addr);
+		return e & kHitMask;
+	}
+	__device__ __forceinline__ uint32_t step(uint32_t sym2) { return step_of(ent, sym2); }
+	// symbols of in-chunk stride i, already shifted to their place in the entry address
+	template <int I>
+	__device__ __forceinline__ uint32_t sym_at() const {
+		constexpr int bit = 32 - 2 * kOff + 2 * K * I; // W[0] holds stream bits 0..31, chunk symbol c sits at bit 32 + 2c
+		constexpr int wi = bit >> 5, sh = bit & 31;
+		if constexpr (sh + 2 * K <= 32)
+			return (sh >= kSS ? (W[wi] >> (sh >= kSS ? sh - kSS : 0)) : (W[wi] << (sh < kSS ? kSS - sh : 0))) & kSymMask2;
+		else // only K = 3 straddles words, and K = 3 tables are never global
+			return __funnelshift_r(W[wi], W[wi + 1], sh - 1) & kSymMask2;
+	}
+	template <int I>
+	__device__ __forceinline__ void stride(uint32_t &e) {
+		uint32_t h = step_of(e, sym_at<I>());
+		if (I == 0 && kOff)
+			h &= ~((1u << kOff) - 1); // symbols in front of the chunk belong to the previous lane
+		hw[I / kGroup] += h << (K * (I % kGroup));
+	}
+	template <int J, int HALF>
+	__device__ __forceinline__ void two_chains(uint32_t &ea, uint32_t &eb) {
+		if constexpr (J < kStrides - HALF) {
+			if constexpr (J < HALF)
+				stride<J>(ea);
+			stride<HALF + J>(eb);
+			two_chains<J + 1, HALF>(ea, eb);
+		}
+	}
+	template <int I>
+	__device__ __forceinline__ void one_chain() {
+		if constexpr (I < kStrides) {
+			stride<I>(ent);
+			one_chain<I + 1>();
+		}
 	}
 
 	__device__ __forceinline__ void load(const ScanArgs &a, const uint8_t *buf, uint32_t *pk, uint32_t &badacc) {
@@ -167,20 +207,26 @@ struct FrontAC : PackedKey {
 				}
 			}
 		}
-#pragma unroll
-		for (int i = 0; i < kStrides; i++) {
-			const int bit = 32 - 2 * kOff + 2 * K * i; // W[0] holds stream bits 0..31, chunk symbol c sits at bit 32 + 2c
-			const int wi = bit >> 5, sh = bit & 31;
-			uint32_t sym2;
-			if (sh + 2 * K <= 32)
-				sym2 = (sh >= kSS ? (W[wi] >> (sh >= kSS ? sh - kSS : 0)) : (W[wi] << (sh < kSS ? kSS - sh : 0))) & kSymMask2;
-			else // only K = 3 straddles words, and K = 3 tables are never global
-				sym2 = __funnelshift_r(W[wi], W[wi + 1], sh - 1) & kSymMask2;
-			uint32_t h = step(sym2);
-			if (i == 0 && kOff)
-				h &= ~((1u << kOff) - 1); // symbols in front of the chunk belong to the previous lane
-			hw[i / kGroup] += h << (K * (i % kGroup));
-		}
+		if constexpr (ILP == 2) {
+			// chain B = strides [kHalf, kStrides); its warm-up reads the (up to 32) symbols in front of them
+			constexpr int kHalf = kStrides / 2;
+			constexpr int bitB = 32 - 2 * kOff + 2 * K * kHalf, wb = bitB >> 5, sb = bitB & 31;
+			static_assert(wb >= 2, "chain B needs two words of history in the chunk");
+			const uint32_t lo = sb ? __funnelshift_r(W[wb - 2], W[wb - 1], sb) : W[wb - 2];
+			const uint32_t hi = sb ? __funnelshift_r(W[wb - 1], W[wb], sb) : W[wb - 1];
+			uint64_t hb = ((uint64_t) hi << 32) | lo; // stream bits [bitB - 64, bitB)
+			const uint32_t nwb = (a_depth - 1 + K - 1) / K;
+			uint32_t eb = 0;
+			if (nwb) {
+				hb >>= 64 - 2 * K * nwb;
+				for (uint32_t i = 0; i < nwb; i++) {
+					(void) step_of(eb, ((uint32_t) hb << kSS) & kSymMask2);
+					hb >>= 2 * K;
+				}
+			}
+			two_chains<0, kHalf>(ent, eb);
+		} else
+			one_chain<0>();
 	}
 
 	__device__ __forceinline__ uint32_t count() const {
@@ -273,7 +319,7 @@ struct FrontWM : PackedKey {
 // ------------------------------------------------------------ dispatch
 cudaError_t launch_scan_packed(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st) {
 	const acwm_scan_params &p = a.prm;
-	if (p.algo == ACWM_ALGO_AC) {
+	if (p.algo == ACWM_ALGO_AC && !p.front_kind) {
 		const bool ex = p.exact_front != 0;
 		if (!a.front_in_smem) {
 			if (p.stride == 2)
@@ -284,6 +330,8 @@ cudaError_t launch_scan_packed(const ScanArgs &a, uint32_t threads, uint32_t sme
 						  : launch_front<FrontAC<1, false, true>, false>(a, threads, smem, grid, st);
 			return cudaErrorInvalidValue;
 		}
+		if (p.stride == 3 && ex && p.ilp == 2) // the automaton of a small set (BASELINE configs[0]): two chains per lane
+			return launch_front<FrontAC<3, true, false, 2>, true>(a, threads, smem, grid, st);
 		switch (p.stride) {
 		case 3: return ex ? launch_front<FrontAC<3, true>, true>(a, threads, smem, grid, st)
 						  : launch_front<FrontAC<3, false>, false>(a, threads, smem, grid, st);

@@ -76,6 +76,15 @@ void remember(const void *key, acwm_matcher *mt, uint64_t sig) {
 	g_by_table[key] = WmEntry{mt, sig};
 }
 
+void forget(const void *key) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	auto it = g_by_table.find(key);
+	if (it != g_by_table.end()) {
+		acwm_free(it->second.mt);
+		g_by_table.erase(it);
+	}
+}
+
 acwm_matcher *lookup(const void *key, uint64_t sig) {
 	std::lock_guard<std::mutex> lk(g_mu);
 	auto it = g_by_table.find(key);
@@ -122,8 +131,11 @@ std::vector<uint8_t> patterns_from_goto(int m, int p_size, int alphabet, const i
 void cuda_ac_common(int variant, int m, unsigned char *text, int n, int p_size, int alphabet, int *state_transition,
 		unsigned int *state_supply, unsigned int *state_final) {
 	(void) state_supply;
-	const uint64_t sig = fnv(state_final, ((size_t) m * p_size + 1) * sizeof(unsigned),
-			fnv(&m, sizeof(m), fnv(&alphabet, sizeof(alphabet))));
+	// the goto table IS the pattern set (two sets can share their terminal-state layout, e.g. any two sets of one
+	// pattern): it is part of the signature, so refilled or recycled arrays never reach a stale matcher
+	const size_t n_states = (size_t) m * p_size + 1;
+	const uint64_t sig = fnv(state_transition, n_states * (size_t) alphabet * sizeof(int),
+			fnv(state_final, n_states * sizeof(unsigned), fnv(&m, sizeof(m), fnv(&alphabet, sizeof(alphabet)))));
 	acwm_matcher *mt = lookup(state_transition, sig);
 	if (!mt) {
 		int p = 0;
@@ -169,6 +181,7 @@ struct ac_table *preproc_ac(unsigned char **pattern, int m, int p_size, int alph
 		fprintf(stderr, "Could not initialize table\n"); // ac/ac.c:235
 		exit(1);
 	}
+	forget(state_transition); // a cuda_acN matcher compiled from the previous content of these arrays
 	unsigned ns = 0, nd = 0;
 	fill_reference_ac_tables((const uint8_t *const *) pattern, m, p_size, alphabet, state_transition, state_supply,
 			state_final, &ns, &nd);

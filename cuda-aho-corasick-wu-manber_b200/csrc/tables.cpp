@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 
@@ -97,8 +98,18 @@ static uint32_t pattern_key(const PatternSet &ps, uint32_t j, bool packed, uint3
 	return mix64to32(pack8_tail(ps.pat(j), ps.len[j], b2));
 }
 
+// How much shared memory the tables of one CTA may take: a CTA that owns its SM, or one of two that share it.
+struct TableProfile {
+	uint32_t stage1_bytes;   // WM stage-1 bitmap
+	uint32_t rmask_bytes;    // WM offset masks
+	uint32_t f2_bits;        // log2 of the stage-2 bitmap (bits)
+};
+static const TableProfile kProfileSingle = {64 * 1024, 32 * 1024, 18};
+static const TableProfile kProfileDual = {32 * 1024, 8 * 1024, 16};
+
 // Stage 2 (suffix bitmap) + verification buckets, shared by WM and truncated AC.
-static void build_verify(const PatternSet &ps, bool packed, const acwm_options &opts, Compiled &c) {
+static void build_verify(const PatternSet &ps, bool packed, const acwm_options &opts, Compiled &c,
+		const TableProfile &prof = kProfileSingle) {
 	acwm_scan_params &prm = c.prm;
 	const uint32_t pd = ps.size();
 	const uint32_t b2 = packed ? std::min<uint32_t>(ps.m_min, 16) : std::min<uint32_t>(ps.m_min, 8);
@@ -109,7 +120,7 @@ static void build_verify(const PatternSet &ps, bool packed, const acwm_options &
 	// measured no faster (profiles/r01d_tune.csv) and every CTA has to load it
 	// shared memory up to 2^18 bits (32 KiB); larger sets get an L2-resident bitmap of up to 2^26 bits
 	uint32_t f2bits = std::min<uint32_t>(std::max<uint32_t>(ceil_log2((uint64_t) pd * 64), 13),
-			(opts.force_smem_tables || pd <= 16384) ? 18 : 26);
+			(opts.force_smem_tables || pd <= 16384) ? prof.f2_bits : 26);
 	if (opts.force_f2_bits)
 		f2bits = std::min<uint32_t>(std::max<uint32_t>(opts.force_f2_bits, 13), 26);
 	if (packed && key_bits <= f2bits) {
@@ -120,7 +131,7 @@ static void build_verify(const PatternSet &ps, bool packed, const acwm_options &
 		prm.f2_mult = kMultF2;
 		prm.f2_sh = 32 - f2bits;
 	}
-	prm.f2_in_smem = f2bits <= 18 ? 1 : 0;
+	prm.f2_in_smem = f2bits <= 18 ? 1 : 0; // (a forced size may exceed the profile: the launch shape decides then)
 	prm.f2_words = (uint32_t) (((uint64_t) 1 << f2bits) / 32);
 	c.filter2.assign(prm.f2_words, 0);
 	// buckets
@@ -258,8 +269,28 @@ static uint32_t full_trie_states(const PatternSet &ps, uint32_t A_hint) {
 	return n;
 }
 
-static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uint32_t budget, Compiled &c,
-		std::string &err) {
+struct WmPlan;
+static double wm_plan_cost(const PatternSet &ps, bool packed, uint32_t stage1_bytes, bool allow_global);
+static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packed, const TableProfile &prof, Compiled &c,
+		std::string &err);
+
+// The automaton that decides a candidate window of the filtered AC front (front_kind 1): the full-depth DFA of the
+// pattern set, failure function folded in, one symbol per lookup, uint32 entries (next row << 1 | final) in global
+// memory.  Walked from the root over the m symbols of a window it ends on a final state iff the window is a pattern.
+static bool build_verify_dfa(const PatternSet &ps, uint32_t A, const uint8_t *cls, Compiled &c) {
+	const uint64_t kMaxBytes = 96ull << 20;
+	Trie t;
+	build_suffix_trie(ps, ps.m_min, A, cls, (uint32_t) (kMaxBytes / (4 * A)), t);
+	if (t.overflow)
+		return false;
+	uint32_t n_rows = 0;
+	build_dfa1(t, c.vdfa, n_rows);
+	c.prm.v_rows = n_rows;
+	return true;
+}
+
+static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uint32_t budget, const TableProfile &prof,
+		Compiled &c, std::string &err) {
 	acwm_scan_params &prm = c.prm;
 	const uint32_t m = ps.m_min;
 	const uint32_t Dmax = std::min<uint32_t>(m, kMaxDepthPacked);
@@ -322,6 +353,23 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 			}
 		}
 	}
+	// A sampled block filter in front of the automaton (front_kind 1): the stage-1 bitmap of the WM compiler says where
+	// a pattern CAN end, and only those windows are walked through the (global, L2-resident) automaton.  What large
+	// sets need -- a dependent L2 lookup per K symbols is 6x slower than the filter (profiles/README.md, c3 vs c3wm) --
+	// and what every set too large for a K = 3 automaton in shared memory gains from.
+	if (opts.force_front != 1 && !opts.force_depth && m >= 3) {
+		const double fcost = wm_plan_cost(ps, true, std::min<uint32_t>(prof.stage1_bytes, budget), !opts.force_smem_tables) + 0.25;
+		if (opts.force_front == 2 || fcost < best_cost - 1e-9) {
+			acwm_options wo = opts;
+			wo.force_stride = 0; // the AC meaning of force_stride (K) does not apply to the filter
+			int rc = compile_wm(ps, wo, true, prof, c, err);
+			if (rc != ACWM_OK)
+				return rc;
+			prm.front_kind = 1;
+			prm.verify_kind = build_verify_dfa(ps, 4, nullptr, c) ? 1 : 0; // too large for a table: the buckets decide
+			return ACWM_OK;
+		}
+	}
 	if (!bestK) {
 		err = "AC: no (stride, depth) fits the table budget";
 		return ACWM_ERR_UNSUPPORTED;
@@ -353,8 +401,10 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 	prm.depth = bestD;
 	prm.exact_front = (bestD == m) ? 1 : 0;
 	prm.n_rows = n_rows;
+	// two chains per lane (scan_packed.cu): the second chain repeats ceil((depth - 1) / K) warm-up lookups
+	prm.ilp = (K == 3 && !global && prm.exact_front && bestD <= 16 && getenv("ACWM_NO_ILP") == nullptr) ? 2 : 1;
 	if (!prm.exact_front)
-		build_verify(ps, true, opts, c);
+		build_verify(ps, true, opts, c, prof);
 	c.info.table_in_smem = global ? 0 : 1;
 	return ACWM_OK;
 }
@@ -487,21 +537,34 @@ static WmPlan plan_wm_stride(const PatternSet &ps, bool packed, uint32_t s, uint
 	return best;
 }
 
-static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packed, uint32_t budget, Compiled &c,
-		std::string &err) {
-	acwm_scan_params &prm = c.prm;
-	const uint32_t pd = ps.size();
-	const uint32_t smem_fbits_max = std::min<uint32_t>(ceil_log2((uint64_t) budget * 8 + 1) - 1, 19);
+static uint32_t smem_fbits_for(uint32_t stage1_bytes) {
+	return std::min<uint32_t>(ceil_log2((uint64_t) stage1_bytes * 8 + 1) - 1, 19);
+}
+
+static WmPlan plan_wm(const PatternSet &ps, bool packed, uint32_t force_stride, uint32_t smem_fbits_max, bool allow_global) {
 	WmPlan plan;
 	for (uint32_t s : {16u, 8u, 4u, 2u, 1u}) {
-		if (opts.force_stride && opts.force_stride != s)
+		if (force_stride && force_stride != s)
 			continue;
 		if (s > ps.m_min)
 			continue;
-		const WmPlan p = plan_wm_stride(ps, packed, s, smem_fbits_max, !opts.force_smem_tables);
+		const WmPlan p = plan_wm_stride(ps, packed, s, smem_fbits_max, allow_global);
 		if (p.cost < plan.cost - 1e-9)
 			plan = p;
 	}
+	return plan;
+}
+
+static double wm_plan_cost(const PatternSet &ps, bool packed, uint32_t stage1_bytes, bool allow_global) {
+	return plan_wm(ps, packed, 0, smem_fbits_for(stage1_bytes), allow_global).cost;
+}
+
+static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packed, const TableProfile &prof, Compiled &c,
+		std::string &err) {
+	acwm_scan_params &prm = c.prm;
+	const uint32_t pd = ps.size();
+	const uint32_t smem_fbits_max = smem_fbits_for(prof.stage1_bytes);
+	const WmPlan plan = plan_wm(ps, packed, opts.force_stride, smem_fbits_max, !opts.force_smem_tables);
 	if (!plan.s) {
 		err = "WM: no sampling stride fits (pattern shorter than the forced stride?)";
 		return ACWM_ERR_INVALID;
@@ -536,7 +599,7 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 	// in shared memory while 2 entries per (pattern, offset) fit 32 KiB, else 8 per pair in L2
 	if (s > 1) {
 		const uint32_t eb = s > 8 ? 2 : 1;
-		const uint32_t rbits_smem_max = eb == 2 ? 14 : 15; // 32 KiB
+		const uint32_t rbits_smem_max = ceil_log2(prof.rmask_bytes / eb + 1) - 1; // 32 KiB: 14 / 15 bits
 		uint32_t rbits = std::max<uint32_t>(ceil_log2((uint64_t) s * pd * 2), 10);
 		prm.r_in_smem = 1;
 		if (rbits > rbits_smem_max) {
@@ -566,58 +629,96 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 					reinterpret_cast<uint16_t *>(c.rmask.data())[ri] |= (uint16_t) (1u << r);
 			}
 	}
-	build_verify(ps, packed, opts, c);
+	build_verify(ps, packed, opts, c, prof);
 	c.info.table_in_smem = plan.in_smem ? 1 : 0;
 	return ACWM_OK;
 }
 
 // ------------------------------------------------------------------ entry point
-int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Compiled &out, std::string &err) {
+static uint32_t smem_tables16(const Compiled &c) {
+	// tables are rounded up to 16 bytes each in shared memory
+	return (c.info.table_in_smem ? (((uint32_t) c.front.size() + 15u) & ~15u) : 0)
+			+ (c.prm.r_in_smem ? (((uint32_t) c.rmask.size() + 15u) & ~15u) : 0)
+			+ (c.prm.f2_in_smem ? (((uint32_t) c.filter2.size() * 4 + 15u) & ~15u) : 0);
+}
+
+// One compilation of the tables under a shared-memory profile (a CTA that owns its SM, or one of two sharing it).
+static int compile_with_profile(int algo, const PatternSet &ps, const acwm_options &opts, bool packed, uint32_t budget,
+		uint32_t ac_budget, TableProfile prof, Compiled &out, std::string &err) {
 	out = Compiled();
 	acwm_scan_params &prm = out.prm;
-	const bool packed = ps.alphabet <= 4 && !opts.force_bytes_path;
 	prm.algo = (uint32_t) algo;
 	prm.packed2bit = packed ? 1 : 0;
 	prm.alphabet = ps.alphabet;
 	prm.m_min = ps.m_min;
 	prm.m_max = ps.m_max;
+	prof.stage1_bytes = std::min(prof.stage1_bytes, budget / 2); // stage-1 bitmap; offset masks and stage 2 take <= 32 KiB each
+	if (algo == ACWM_ALGO_AC) {
+		return packed ? compile_ac_packed(ps, opts, ac_budget, prof, out, err) : compile_ac_bytes(ps, opts, ac_budget, out, err);
+	}
+	return compile_wm(ps, opts, packed, prof, out, err);
+}
+
+int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Compiled &out, std::string &err) {
+	const bool packed = ps.alphabet <= 4 && !opts.force_bytes_path;
 	uint32_t budget = opts.smem_table_budget ? opts.smem_table_budget : kDefaultTableBudget;
 	const uint32_t hard_cap = kMaxSmem - kSmemReserve - 4 * warp_smem_bytes(2, packed);
 	budget = std::min(budget, hard_cap);
-	int rc;
-	if (algo == ACWM_ALGO_AC) {
-		if (ps.m_min != ps.m_max) {
-			err = "Aho-Corasick path takes equal-length patterns (preproc_ac has a single m, ac/ac.c:224); "
-				  "use ACWM_ALGO_WM for mixed lengths";
-			return ACWM_ERR_UNSUPPORTED;
-		}
-		// leave room for the stage-2 bitmap in case the automaton gets truncated
-		const uint32_t ac_budget = budget > 64 * 1024 ? budget - 32 * 1024 : budget / 2;
-		rc = packed ? compile_ac_packed(ps, opts, ac_budget, out, err) : compile_ac_bytes(ps, opts, ac_budget, out, err);
-	} else if (algo == ACWM_ALGO_WM) {
-		const uint32_t wm_budget = budget / 2; // stage-1 bitmap; the offset masks and the stage-2 bitmap take <= 32 KiB each
-		rc = compile_wm(ps, opts, packed, wm_budget, out, err);
-	} else {
+	if (algo != ACWM_ALGO_AC && algo != ACWM_ALGO_WM) {
 		err = "unknown algorithm id";
 		return ACWM_ERR_INVALID;
 	}
+	if (algo == ACWM_ALGO_AC && ps.m_min != ps.m_max) {
+		err = "Aho-Corasick path takes equal-length patterns (preproc_ac has a single m, ac/ac.c:224); "
+			  "use ACWM_ALGO_WM for mixed lengths";
+		return ACWM_ERR_UNSUPPORTED;
+	}
+	// AC: leave room for the stage-2 bitmap in case the automaton gets truncated
+	const uint32_t ac_budget = budget > 64 * 1024 ? budget - 32 * 1024 : budget / 2;
+	int rc = compile_with_profile(algo, ps, opts, packed, budget, ac_budget, kProfileSingle, out, err);
 	if (rc != ACWM_OK)
 		return rc;
-	// tables are rounded up to 16 bytes each in shared memory
-	const uint32_t smem_tables16 = (out.info.table_in_smem ? (((uint32_t) out.front.size() + 15u) & ~15u) : 0)
-			+ (prm.r_in_smem ? (((uint32_t) out.rmask.size() + 15u) & ~15u) : 0)
-			+ (prm.f2_in_smem ? (((uint32_t) out.filter2.size() * 4 + 15u) & ~15u) : 0);
-	LaunchShape shape = shape_for_tables(smem_tables16, packed);
-	if (opts.force_threads || opts.force_stages) { // tuning / tests
+	const bool forced_shape = opts.force_threads || opts.force_stages;
+	LaunchShape shape = shape_for_tables(smem_tables16(out), packed, packed && !out.prm.exact_front);
+	// Two half-size CTAs per SM (2-bit path): consecutive scans of a stream then share every SM in overlap mode.
+	// Taken when the tables fit twice WITHOUT a less selective plan: same stride, block and bitmap sizes as the
+	// single-CTA compilation (the offset masks alone may shrink to one entry per (pattern, offset) pair).
+	if (packed && opts.force_ctas != 1 && !forced_shape && ps.size() <= 16384) {
+		Compiled dual;
+		std::string derr;
+		// an exact automaton needs no 2-bit copy of the tile: what 12 warps leave of half an SM (minus 1 KiB of per-tile counts)
+		const uint32_t ac_dual = std::min(ac_budget, kMaxSmemDual - kSmemReserve - 12 * warp_smem_bytes(1, false) - 1024);
+		if (compile_with_profile(algo, ps, opts, packed, std::min(budget, 2 * kProfileDual.stage1_bytes), ac_dual, kProfileDual,
+					dual, derr) == ACWM_OK) {
+			const acwm_scan_params &a = out.prm, &b = dual.prm;
+			const bool same_plan = a.stride == b.stride && a.depth == b.depth && a.exact_front == b.exact_front
+					&& a.front_kind == b.front_kind && dual.front.size() == out.front.size()
+					&& dual.info.table_in_smem == out.info.table_in_smem && a.f2_words == b.f2_words
+					&& a.r_in_smem == b.r_in_smem && a.f2_in_smem == b.f2_in_smem
+					&& (b.r_entries == a.r_entries || (uint64_t) b.stride * ps.size() <= b.r_entries);
+			const LaunchShape ds = shape_for_tables(smem_tables16(dual), true, !b.exact_front, true);
+			if (ds.warps && (same_plan || opts.force_ctas == 2)) {
+				out = std::move(dual);
+				shape = ds;
+			}
+		}
+		if (opts.force_ctas == 2 && shape.ctas != 2) {
+			err = "force_ctas = 2: the scan tables do not fit shared memory twice";
+			return ACWM_ERR_INVALID;
+		}
+	}
+	const bool pk_copy = packed && !out.prm.exact_front;
+	if (forced_shape) { // tuning / tests
 		LaunchShape want{opts.force_threads ? opts.force_threads / 32 : shape.warps,
-				opts.force_stages ? opts.force_stages : shape.stages};
+				opts.force_stages ? opts.force_stages : shape.stages, opts.force_ctas == 2 ? 2u : 1u};
 		const bool ok = (want.warps == 32 || want.warps == 24 || want.warps == 16 || want.warps == 12 || want.warps == 8
 								|| want.warps == 4)
 				&& want.warps * 32 == (opts.force_threads ? opts.force_threads : want.warps * 32)
 				&& want.stages >= (packed ? 1u : 2u) && want.stages <= kMaxStages
-				&& shape_fits(smem_tables16, want, packed);
+				&& (want.ctas == 1 || (packed && (want.warps == 16 || want.warps == 12)))
+				&& shape_fits(smem_tables16(out), want, pk_copy);
 		if (!ok) {
-			err = "forced launch shape (threads / stages) not available for this table size";
+			err = "forced launch shape (threads / stages / CTAs per SM) not available for this table size";
 			return ACWM_ERR_INVALID;
 		}
 		shape = want;
@@ -626,7 +727,7 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 		err = "scan tables exceed shared memory";
 		return ACWM_ERR_UNSUPPORTED;
 	}
-	const uint32_t threads = shape.warps * 32;
+	const acwm_scan_params &prm = out.prm;
 	acwm_info &inf = out.info;
 	inf.algo = (uint32_t) algo;
 	inf.alphabet = ps.alphabet;
@@ -638,13 +739,17 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 	inf.stride = prm.stride;
 	inf.depth = prm.depth;
 	inf.exact_front = prm.exact_front;
-	inf.n_rows = prm.n_rows;
+	inf.n_rows = prm.front_kind ? prm.v_rows : prm.n_rows;
 	inf.n_states = (algo == ACWM_ALGO_AC) ? full_trie_states(ps, ps.alphabet) : 0;
-	inf.threads = threads;
+	inf.threads = shape.warps * 32;
 	inf.stages = shape.stages;
-	inf.smem_bytes = smem_tables16 + shape.warps * warp_smem_bytes(shape.stages, packed) + kSmemReserve;
+	inf.ctas_per_sm = shape.ctas;
+	inf.front_kind = prm.front_kind;
+	inf.smem_bytes = shape_smem(smem_tables16(out), shape, pk_copy);
+	if (shape.ctas == 2) // never three CTAs on an SM: the bound on scans in flight (Work, scan_common.cuh) rests on it
+		inf.smem_bytes = std::max(inf.smem_bytes, kMinSmemDual);
 	inf.table_bytes = out.front.size() + out.rmask.size() + out.filter2.size() * 4 + out.bucket_start.size() * 4
-			+ out.entries.size() * sizeof(acwm_ventry) + ps.bytes.size();
+			+ out.entries.size() * sizeof(acwm_ventry) + ps.bytes.size() + out.vdfa.size() * 4;
 	return ACWM_OK;
 }
 

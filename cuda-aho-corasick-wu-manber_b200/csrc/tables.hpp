@@ -39,6 +39,7 @@ struct Compiled {
 	std::vector<uint32_t> bucket_start;  // n_buckets + 1
 	std::vector<acwm_ventry> entries;
 	std::vector<uint8_t> symclass;       // bytes-path AC: 256 entries
+	std::vector<uint32_t> vdfa;          // filtered AC: full-depth one-symbol DFA that decides candidate windows
 	uint32_t front_entry_bytes = 2;
 };
 

@@ -70,7 +70,10 @@ typedef struct acwm_options {
 	uint32_t force_f2_bits;     /* log2 of the stage-2 bitmap size in bits, 13..19 (tuning); 0 = auto */
 	uint32_t force_r_bits;      /* log2 of the number of WM offset-mask entries, 10..16 (tuning); 0 = auto */
 	uint32_t force_smem_tables; /* 1 = never place a scan table in global memory (L2), whatever the set size */
-	uint32_t reserved;
+	uint32_t force_front;       /* AC, 2-bit path: 1 = the automaton walks every symbol, 2 = sampled block filter in front and the
+	                             * automaton walks candidate windows only; 0 = auto (cost model) */
+	uint32_t force_ctas;        /* CTAs per SM of the scan kernel: 1, or 2 (half-size CTAs of consecutive scans share every SM
+	                             * in overlap mode; 2-bit path only); 0 = auto */
 } acwm_options;
 
 /* What the builder chose; for reports and tests. */
@@ -87,6 +90,9 @@ typedef struct acwm_info {
 	uint64_t table_bytes;   /* bytes of device tables */
 	uint32_t threads;       /* threads per CTA of the scan kernel */
 	uint32_t stages;        /* tiles in flight per warp (TMA ring depth) */
+	uint32_t ctas_per_sm;   /* 1: one CTA owns the SM; 2: two half-size CTAs share it (acwm_set_overlap) */
+	uint32_t front_kind;    /* 0: the automaton / the block filter named by `algo` walks every symbol;
+	                         * 1: AC behind a sampled block filter -- the automaton walks candidate windows only */
 } acwm_info;
 
 /* ------------------------------ native API ------------------------------ */
@@ -223,7 +229,8 @@ enum {
 	ACWM_BLOB_PATTERNS = 4,   /* distinct pattern bytes, back to back */
 	ACWM_BLOB_PARAMS = 5,     /* acwm_scan_params */
 	ACWM_BLOB_SYMCLASS = 6,   /* bytes path AC: 256-entry symbol -> class map */
-	ACWM_BLOB_RMASK = 7       /* WM, stride > 1: offset masks of the candidate blocks (uint8, uint16 for stride 16) */
+	ACWM_BLOB_RMASK = 7,      /* WM, stride > 1: offset masks of the candidate blocks (uint8, uint16 for stride 16) */
+	ACWM_BLOB_VDFA = 8        /* filtered AC: full-depth one-symbol DFA, uint32 entries (next row << 1 | final) */
 };
 int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_t *bytes);
 
@@ -274,7 +281,11 @@ typedef struct acwm_scan_params {
 	uint32_t n_classes;     /* bytes path AC */
 	uint32_t r_mult, r_sh, r_entries, r_entry_bytes; /* WM offset masks: ridx = (block * mult) >> sh; 0 entries = none */
 	uint32_t r_in_smem, f2_in_smem; /* 1: the table is staged in shared memory, 0: read from global memory (L2-resident) */
-	uint32_t reserved[2];
+	uint32_t front_kind;    /* AC: 0 = the automaton walks every symbol, 1 = WM-style block filter in front, the
+	                         * automaton decides candidate windows only */
+	uint32_t verify_kind;   /* what decides a candidate window: 0 = hash buckets + compare, 1 = walk of the verify DFA */
+	uint32_t v_rows;        /* rows of the verify DFA (ACWM_BLOB_VDFA) */
+	uint32_t ilp;           /* AC, exact K = 3 automaton in shared memory: 2 = every lane walks its chunk as two independent chains */
 } acwm_scan_params;
 
 /* ------------------- reference-shaped shims (smatcher.h) ------------------- */

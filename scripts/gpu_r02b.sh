@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round 2, session b: two CTAs per SM + two-chain AC walk + filtered AC: parity subset, then step times
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+exec > >(tee gpurun_out/r02b.log) 2>&1
+nproc; nvidia-smi -L
+echo "=== parity subset ==="
+timeout 1200 python -m pytest tests -m gpu -x -q -k "random_cases or edge_cases or overlapped or dense_matches or launch_shape or unaligned" 2>&1 | tail -15
+rm -f gpurun_out/probe_warps.csv
+echo "=== step times: default / one CTA per SM ==="
+PROBE_OPTS='[{}, {"force_ctas": 1}]' timeout 600 python scripts/probe_warps.py c1,c2,c2ac,c3,c3wm 100
+echo "=== c1 without the two-chain walk ==="
+ACWM_NO_ILP=1 PROBE_OPTS='[{}, {"force_ctas": 1}]' timeout 600 python scripts/probe_warps.py c1 100

@@ -72,3 +72,22 @@ gap = (T[3:, :, 0].min(1) - T[2:-1, :, 8].max(1)) / 1e3
 log(f"  next launch's first entry minus this launch's last exit: {np.round(gap, 2)}")
 step = np.diff(T[:, :, 8].max(1)) / 1e3
 log(f"  last-exit to last-exit (step time): {np.round(step, 2)}")
+# who shares an SM: for every SM the [entry, exit] intervals of the CTAs of all traced launches, in time order
+sm = T[:, :, 11].astype(np.int64)
+log()
+log("per-SM occupancy (first 4 SMs): launch:cta [entry .. scan done .. exit] in us")
+for s_ in sorted(set(sm.reshape(-1).tolist()))[:4]:
+    rows = sorted((T[k, c, 0], k, c) for k in range(NL) for c in range(G) if sm[k, c] == s_)
+    log(f"  SM {s_}: " + "  ".join(f"{k}:{c} [{(T[k,c,0]-t0)/1e3:.1f} .. {(T[k,c,4]-t0)/1e3:.1f} .. {(T[k,c,8]-t0)/1e3:.1f}]" for _, k, c in rows))
+conc = []
+for k in range(1, NL):
+    for c in range(G):
+        others = [(kk, cc) for kk in range(NL) for cc in range(G) if (kk, cc) != (k, c) and sm[kk, cc] == sm[k, c]
+                  and T[kk, cc, 0] < T[k, c, 8] and T[kk, cc, 8] > T[k, c, 0]]
+        conc.append(len(others))
+log(f"  CTAs of other traced launches that overlap a CTA's lifetime on its SM: mean {np.mean(conc):.2f} max {max(conc)}")
+inflight = []
+for k in range(NL):
+    lo, hi = T[k, :, 0].min(), T[k, :, 8].max()
+    inflight.append(sum(1 for kk in range(NL) if T[kk, :, 0].min() < hi and T[kk, :, 8].max() > lo))
+log(f"  launches in flight during each launch (incl. itself): {inflight}")

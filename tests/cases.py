@@ -51,6 +51,20 @@ RANDOM_CASES = [
     ("wm_ascii_p10000_m12_smem_only", WM, 256, 10000, 12, 100_000, dict(force_smem_tables=1)),
     ("c3_ac_dna_p100000_m32", AC, 4, 100000, 32, 60_000, {}),
     ("ac_dna_p10000_m16_f2_l2", AC, 4, 10000, 16, 100_000, {}),
+    # AC front ends pinned down: the automaton walks every symbol (force_front=1: shared memory, truncated, or the
+    # L2-resident one) / a sampled block filter in front and the automaton decides candidate windows (force_front=2)
+    ("ac_dna_p1000_m16_walk", AC, 4, 1000, 16, 200_000, dict(force_front=1)),
+    ("c3_ac_dna_p100000_m32_walk_l2", AC, 4, 100000, 32, 60_000, dict(force_front=1)),
+    ("ac_dna_p10000_m16_walk_l2", AC, 4, 10000, 16, 100_000, dict(force_front=1)),
+    ("c1_ac_dna_p100_m8_filtered", AC, 4, 100, 8, 300_000, dict(force_front=2)),
+    ("ac_dna_p1000_m16_filtered", AC, 4, 1000, 16, 200_000, dict(force_front=2)),
+    ("ac_dna_p300_m3_filtered", AC, 4, 40, 3, 100_000, dict(force_front=2)),
+    ("ac_bin_p10_m12_filtered", AC, 2, 10, 12, 50_000, dict(force_front=2)),
+    # one CTA per SM / two half-size CTAs per SM
+    ("c1_ac_one_cta", AC, 4, 100, 8, 300_000, dict(force_ctas=1)),
+    ("c2_wm_one_cta", WM, 4, 1000, 16, 300_000, dict(force_ctas=1)),
+    ("c1_ac_two_ctas", AC, 4, 100, 8, 300_000, dict(force_ctas=2)),
+    ("c2_wm_two_ctas", WM, 4, 1000, 16, 300_000, dict(force_ctas=2)),
 ]
 
 

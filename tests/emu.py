@@ -37,6 +37,7 @@ class Emulator:
         rm = mt.blob(acwm.BLOB_RMASK)
         self.rmask = rm.view(np.uint16 if self.p.r_entry_bytes == 2 else np.uint8) if rm.size else None
         self.info = mt.info
+        self.vdfa = mt.blob(acwm.BLOB_VDFA).view(np.uint32) if self.p.verify_kind else None
 
     # ------------------------------------------------------------ windows
     def _win16(self, sym):
@@ -64,6 +65,17 @@ class Emulator:
         i2 = _mul32(keys, p.f2_mult) >> np.uint64(p.f2_sh)
         bits = (self.f2[(i2 >> np.uint64(5)).astype(np.int64)] >> (i2 & np.uint64(31)).astype(np.uint32)) & 1
         out = []
+        if p.verify_kind:  # filtered AC: the window is walked through the full-depth automaton from its root (verify_dfa)
+            m = p.m_min
+            for e in ends[bits == 1].tolist():
+                if e + 1 < m or e >= n:
+                    continue
+                ent = 0
+                for c in text[e + 1 - m:e + 1].tolist():
+                    ent = int(self.vdfa[(ent >> 1) * 4 + (c & 3)])
+                if ent & 1:
+                    out.append((e, 1))
+            return out
         for e, key in zip(ends[bits == 1].tolist(), keys[bits == 1].tolist()):
             b = ((key * p.hb_mult) & 0xFFFFFFFF) >> p.hb_sh
             mult = 0
@@ -150,7 +162,7 @@ class Emulator:
             assert int(text.max()) < 4, "bad text for the 2-bit path"
             sym = text.astype(np.int64)
             win = self._win16(text)
-            if p.algo == acwm.AC:
+            if p.algo == acwm.AC and not p.front_kind:
                 # entry = byte offset of the next row | hits (uint16 in shared memory, uint32 in global memory)
                 hits = self._ac_hits(sym, 112, 2, 1 << (2 * p.stride),
                                      2 * p.stride + (1 if self.info["table_in_smem"] else 2))

@@ -123,7 +123,7 @@ def test_overlapped_back_to_back_scans(acwm, oracle, torch_cuda):
         case = next(c for c in RANDOM_CASES if c[0] == cname)
         name, algo, alphabet, p, m, n, opts = case
         pats, text = make_case(case)
-        big = np.concatenate([text] * 24)  # ~6 MB: enough tiles for every CTA
+        big = np.concatenate([text] * 100)  # 15-30 MB: enough tiles for every warp of every CTA (the launches chain)
         other = dg.text_host(big.size - 12345, alphabet, 77)
         other[1000:1000 + pats.shape[1]] = pats[0]
         refs = [oracle.set_search(pats, t) for t in (big, other)]
@@ -409,6 +409,20 @@ def test_reference_shaped_shims(acwm, oracle, torch_cuda, capfd):
         assert sm.cuda_ac(k, m, text, n, p, alphabet, state_transition, state_supply, state_final) == want
     out = capfd.readouterr().out
     assert f"Kernel 5 matches \t{want}\t time" in out
+    # the caller refills the SAME arrays with another set of the same terminal-state layout (one pattern: state m is
+    # final either way): the goto table is part of the matcher's cache key, so the new set is what gets searched
+    one_a, one_b = pattern[:1].copy(), pattern[5:6].copy()
+    text1 = text.copy()
+    text1[100:100 + m], text1[500:500 + m], text1[900:900 + m] = one_a[0], one_b[0], one_b[0]
+    tr_a, sup_a, fin_a = sm.alloc_ac_tables(m, 1, alphabet)
+    sm.free_ac(sm.preproc_ac(one_a, m, 1, alphabet, tr_a, sup_a, fin_a), alphabet)
+    assert sm.cuda_ac(5, m, text1, n, 1, alphabet, tr_a, sup_a, fin_a) == oracle.set_search(one_a, text1)["count"]
+    tr_b, sup_b, fin_b = sm.alloc_ac_tables(m, 1, alphabet)
+    sm.free_ac(sm.preproc_ac(one_b, m, 1, alphabet, tr_b, sup_b, fin_b), alphabet)
+    assert np.array_equal(fin_a, fin_b) and not np.array_equal(tr_a, tr_b)
+    np.copyto(tr_a, tr_b), np.copyto(sup_a, sup_b)
+    assert sm.cuda_ac(5, m, text1, n, 1, alphabet, tr_a, sup_a, fin_a) == oracle.set_search(one_b, text1)["count"]
+    capfd.readouterr()
     # multiwm / multiwm2 + cuda_wm
     case = RANDOM_CASES[1]
     name, algo, alphabet, p, m, n, opts = case
