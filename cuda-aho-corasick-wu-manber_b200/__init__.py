@@ -105,6 +105,13 @@ def lib():
         L.acwm_device_count.restype = C.c_int
         L.acwm_search_host_sharded.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint64, _u64p,
                                                C.c_void_p, C.c_uint64, _u64p, _u64p]
+        L.acwm_peers_create.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
+        L.acwm_peers_destroy.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
+        L.acwm_scan_device_sharded.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_void_p), _u64p, C.c_int]
+        L.acwm_fetch_sharded.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, _u64p, _u64p]
+        L.acwm_text_to_device.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.acwm_device_free.argtypes = [C.c_int, C.c_void_p]
+        L.acwm_device_free.restype = None
         L.acwm_set_trace.argtypes = [C.c_void_p, C.c_void_p]
         L.acwm_pack_text_2bit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_int)]
         L.acwm_trace_words_per_cta.restype = C.c_uint32
@@ -173,6 +180,44 @@ def search_host_sharded(matchers, text, cap: int | None = None, want_positions: 
                                           per.ctypes.data_as(_u64p)),
            allow=(ERR_OVERFLOW,) if allow_overflow else ())
     return int(count.value), pos[:int(nw.value)], per
+
+
+def _handles(matchers):
+    return (C.c_void_p * len(matchers))(*[m._h for m in matchers])
+
+
+def peers_create(matchers):
+    """Wire the in-kernel count exchange between uploaded matchers of ONE process (``acwm_peers_create``): mailboxes
+    by cudaMalloc, peer access between their devices -- no torch, NCCL or MPI involved."""
+    _check(lib().acwm_peers_create(_handles(matchers), len(matchers)))
+
+
+def peers_destroy(matchers):
+    _check(lib().acwm_peers_destroy(_handles(matchers), len(matchers)))
+
+
+def scan_device_sharded(matchers, shards, want_positions: bool = True):
+    """One scan of every device-resident shard (``acwm_scan_device_sharded``); shards[r] = CUDA uint8 tensor on
+    matchers[r]'s device holding shard r with its halo, or a (device pointer, length) pair."""
+    ptrs, lens = [], []
+    for sh in shards:
+        if hasattr(sh, "data_ptr"):
+            ptrs.append(sh.data_ptr())
+            lens.append(sh.numel())
+        else:
+            ptrs.append(int(sh[0]))
+            lens.append(int(sh[1]))
+    pa = (C.c_void_p * len(ptrs))(*ptrs)
+    la = (C.c_uint64 * len(lens))(*lens)
+    _check(lib().acwm_scan_device_sharded(_handles(matchers), len(matchers), pa, la, int(want_positions)))
+
+
+def fetch_sharded(matchers):
+    """-> (global count as exchanged inside the kernels, per-shard counts)."""
+    g = C.c_uint64()
+    per = np.zeros(len(matchers), np.uint64)
+    _check(lib().acwm_fetch_sharded(_handles(matchers), len(matchers), C.byref(g), per.ctypes.data_as(_u64p)))
+    return int(g.value), per
 
 
 class Matcher:

@@ -85,6 +85,9 @@ static int ensure_tiles(acwm_matcher *mt, uint64_t n_tiles) {
 	return ACWM_OK;
 }
 
+static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
+		uint64_t tile_hi, int want_positions, int append, int exchange, cudaStream_t st, int packed_in = 0);
+
 static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 	if (device >= 0)
 		CU(cudaSetDevice(device));
@@ -145,8 +148,14 @@ static int do_upload(acwm_matcher *mt, int device, uint64_t pos_capacity) {
 		(void) cudaGetLastError();
 	}
 	mt->uploaded = true;
-	if (pos_capacity)
-		return ensure_positions(mt, pos_capacity);
+	if (pos_capacity && (rc = ensure_positions(mt, pos_capacity)))
+		return rc;
+	// One empty scan now: the kernel's module is loaded and its attributes are set here, not inside the first search
+	// (whose event-bracketed kernel time, acwm_last_kernel_seconds, is kernel-only like the reference's gpuTime,
+	// cuda/cuda_wm.cu:264-289)
+	if ((rc = launch_scan(mt, mt->d_tables, 0, 0, 0, 0, 0, 0, 0, mt->s_scan)))
+		return rc;
+	CU(cudaStreamSynchronize(mt->s_scan));
 	return ACWM_OK;
 }
 
@@ -179,7 +188,7 @@ static uint32_t kernel_tune() {
 // Launch the scan of warp tiles [tile_lo, tile_hi) of the text at d_text (n bytes): one
 // kernel that scans, orders the positions and publishes the result block.
 static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint64_t report_from, uint64_t tile_lo,
-		uint64_t tile_hi, int want_positions, int append, int exchange, cudaStream_t st, int packed_in = 0) {
+		uint64_t tile_hi, int want_positions, int append, int exchange, cudaStream_t st, int packed_in) {
 	const Compiled &c = mt->c;
 	ScanArgs a;
 	memset(&a, 0, sizeof(a));
@@ -257,8 +266,12 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 // Sum of the mailbox for the last exchange epoch (the scan kernels collect epoch x-1 while they run epoch x).
 __global__ void collect_last_kernel(Control *ctl, const unsigned long long *box, uint32_t world, uint32_t x) {
 	if (ctl->result.global_epoch != x) {
-		ctl->result.global_count = collect_mailbox(box, world, x);
-		ctl->result.global_epoch = x;
+		unsigned long long sum;
+		if (collect_mailbox(box, world, x, sum)) {
+			ctl->result.global_count = sum;
+			ctl->result.global_epoch = x;
+		} else
+			ctl->result.exchange_failed = x;
 	}
 }
 
@@ -699,6 +712,10 @@ int acwm_fetch_global_count(acwm_matcher *mt, uint64_t *global_count, void *stre
 	CU(cudaMemcpyAsync(mt->h_res, &mt->d_ctl->result, sizeof(Result), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	*global_count = mt->h_res->global_count;
+	if (mt->peer_world > 1 && mt->h_res->exchange_failed) {
+		CU(cudaMemsetAsync(&mt->d_ctl->result.exchange_failed, 0, sizeof(unsigned int), st));
+		return set_error(ACWM_ERR_CUDA, "count exchange: a peer's count did not arrive (it skipped a scan, failed before its launch, or died)");
+	}
 	return ACWM_OK;
 }
 
@@ -766,6 +783,8 @@ void acwm_free(acwm_matcher *mt) {
 			cudaFreeHost(mt->h_hist);
 		if (mt->d_raw)
 			cudaFree(mt->d_raw);
+		if (mt->d_mailbox)
+			cudaFree(mt->d_mailbox);
 		if (mt->s_copy2)
 			cudaStreamDestroy(mt->s_copy2);
 		for (auto e : mt->ev_pack)
@@ -963,6 +982,159 @@ int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uin
 	if (n_written)
 		*n_written = w;
 	return rc == ACWM_OK ? ACWM_OK : set_error(rc, err);
+}
+
+// ---- one process, several GPUs, device-resident shards: the count exchange of the scan kernels without torch / NCCL
+static int check_shard_set(acwm_matcher *const *mts, uint32_t world, const char *who) {
+	if (!mts || world == 0 || world > kMaxPeers)
+		return set_error(ACWM_ERR_INVALID, std::string(who) + ": NULL argument or world not in 1..16");
+	for (uint32_t r = 0; r < world; r++) {
+		if (!mts[r] || !mts[r]->uploaded)
+			return set_error(ACWM_ERR_INVALID, std::string(who) + ": every matcher must be uploaded (acwm_upload) first");
+		for (uint32_t q = 0; q < r; q++)
+			if (mts[q] == mts[r])
+				return set_error(ACWM_ERR_INVALID, std::string(who) + ": one matcher per shard");
+	}
+	return ACWM_OK;
+}
+
+int acwm_peers_destroy(acwm_matcher *const *mts, uint32_t world) {
+	if (!mts)
+		return set_error(ACWM_ERR_INVALID, "acwm_peers_destroy: NULL argument");
+	for (uint32_t r = 0; r < world; r++) {
+		acwm_matcher *mt = mts[r];
+		if (!mt)
+			continue;
+		mt->peer_world = mt->peer_rank = 0;
+		mt->shard_stream = nullptr;
+		if (mt->d_mailbox && mt->uploaded) {
+			cudaSetDevice(mt->device);
+			cudaStreamSynchronize(mt->s_scan);
+			cudaFree(mt->d_mailbox);
+			(void) cudaGetLastError();
+		}
+		mt->d_mailbox = nullptr;
+	}
+	return ACWM_OK;
+}
+
+int acwm_peers_create(acwm_matcher *const *mts, uint32_t world) {
+	int rc = check_shard_set(mts, world, "acwm_peers_create");
+	if (rc != ACWM_OK)
+		return rc;
+	acwm_peers_destroy(mts, world);
+	for (uint32_t r = 0; r < world; r++)
+		for (uint32_t q = 0; q < world; q++) {
+			const int dr = mts[r]->device, dq = mts[q]->device;
+			if (dr == dq)
+				continue;
+			int can = 0;
+			CU(cudaDeviceCanAccessPeer(&can, dr, dq));
+			if (!can)
+				return set_error(ACWM_ERR_UNSUPPORTED, "acwm_peers_create: device " + std::to_string(dr)
+						+ " cannot access the memory of device " + std::to_string(dq));
+			CU(cudaSetDevice(dr));
+			const cudaError_t e = cudaDeviceEnablePeerAccess(dq, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+				return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+			(void) cudaGetLastError();
+		}
+	uint64_t ptrs[kMaxPeers] = {};
+	const size_t box_bytes = (size_t) kPeerRing * world * sizeof(unsigned long long);
+	for (uint32_t r = 0; r < world; r++) {
+		acwm_matcher *mt = mts[r];
+		CU(cudaSetDevice(mt->device));
+		CU(cudaMalloc((void **) &mt->d_mailbox, box_bytes));
+		CU(cudaMemset(mt->d_mailbox, 0, box_bytes));
+		CU(cudaDeviceSynchronize());
+		ptrs[r] = (uint64_t) (uintptr_t) mt->d_mailbox;
+	}
+	for (uint32_t r = 0; r < world; r++) {
+		if ((rc = acwm_set_peers(mts[r], r, world, ptrs)))
+			return rc;
+		// matchers of one device share the stream of the first of them: their scans then run in rank order, so a
+		// kernel that collects the previous exchange never waits for a kernel queued behind it on the same GPU
+		mts[r]->shard_stream = mts[r]->s_scan;
+		for (uint32_t q = 0; q < r; q++)
+			if (mts[q]->device == mts[r]->device) {
+				mts[r]->shard_stream = mts[q]->shard_stream;
+				break;
+			}
+	}
+	return ACWM_OK;
+}
+
+int acwm_scan_device_sharded(acwm_matcher *const *mts, uint32_t world, const uint8_t *const *d_shards,
+		const uint64_t *shard_lens, int want_positions) {
+	int rc = check_shard_set(mts, world, "acwm_scan_device_sharded");
+	if (rc != ACWM_OK)
+		return rc;
+	if (!d_shards || !shard_lens)
+		return set_error(ACWM_ERR_INVALID, "acwm_scan_device_sharded: NULL argument");
+	const uint32_t m_max = mts[0]->c.prm.m_max;
+	for (uint32_t r = 0; r < world; r++) {
+		acwm_matcher *mt = mts[r];
+		if (world > 1 && (mt->peer_world != world || mt->peer_rank != r))
+			return set_error(ACWM_ERR_INVALID, "acwm_scan_device_sharded: call acwm_peers_create on these matchers first");
+		CU(cudaSetDevice(mt->device));
+		cudaStream_t st = mt->shard_stream ? mt->shard_stream : mt->s_scan;
+		if ((rc = acwm_scan_device(mt, d_shards[r], shard_lens[r], r ? (uint64_t) (m_max - 1) : 0, want_positions, st)))
+			return rc;
+	}
+	return ACWM_OK;
+}
+
+int acwm_fetch_sharded(acwm_matcher *const *mts, uint32_t world, uint64_t *global_count, uint64_t *shard_counts) {
+	int rc = check_shard_set(mts, world, "acwm_fetch_sharded");
+	if (rc != ACWM_OK)
+		return rc;
+	for (uint32_t r = 0; r < world; r++) { // every scan has published before anybody collects
+		CU(cudaSetDevice(mts[r]->device));
+		CU(cudaStreamSynchronize(mts[r]->shard_stream ? mts[r]->shard_stream : mts[r]->s_scan));
+	}
+	uint64_t total = 0, first = 0;
+	for (uint32_t r = 0; r < world; r++) {
+		acwm_matcher *mt = mts[r];
+		CU(cudaSetDevice(mt->device));
+		uint64_t g = 0;
+		if ((rc = acwm_fetch_global_count(mt, &g, mt->shard_stream ? mt->shard_stream : mt->s_scan)))
+			return rc;
+		if (mt->h_res->order_failed > mt->first_epoch)
+			return set_error(ACWM_ERR_CUDA, "the position ordering gave up waiting for a CTA of its own launch");
+		if (mt->h_res->bad_text)
+			return set_error(ACWM_ERR_BAD_TEXT, "text holds a byte >= 4 but the matcher was built for alphabet <= 4");
+		if (shard_counts)
+			shard_counts[r] = mt->h_res->count;
+		total += mt->h_res->count;
+		if (r == 0)
+			first = g;
+		else if (g != first)
+			return set_error(ACWM_ERR_CUDA, "count exchange: the shards disagree on the global count");
+	}
+	if (first != total)
+		return set_error(ACWM_ERR_CUDA, "count exchange: the exchanged sum differs from the sum of the shard counts");
+	if (global_count)
+		*global_count = first;
+	return ACWM_OK;
+}
+
+int acwm_text_to_device(int device, const uint8_t *text, uint64_t n, uint8_t **d_text) {
+	if (!d_text || (!text && n))
+		return set_error(ACWM_ERR_INVALID, "acwm_text_to_device: NULL argument");
+	*d_text = nullptr;
+	CU(cudaSetDevice(device));
+	CU(cudaMalloc((void **) d_text, n ? n : 16));
+	if (n)
+		CU(cudaMemcpy(*d_text, text, n, cudaMemcpyHostToDevice));
+	return ACWM_OK;
+}
+
+void acwm_device_free(int device, void *d_ptr) {
+	if (!d_ptr)
+		return;
+	if (cudaSetDevice(device) == cudaSuccess)
+		cudaFree(d_ptr);
+	(void) cudaGetLastError();
 }
 
 int acwm_table_blob(const acwm_matcher *mt, int which, const void **ptr, uint64_t *bytes) {

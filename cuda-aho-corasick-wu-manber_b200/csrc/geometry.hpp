@@ -46,11 +46,12 @@ constexpr uint32_t kStageBlock = 1u << kStageBlockLog2; // staging slots of a wa
 
 // (warps, stages, CTAs per SM) the scan kernel is launched with, in order of preference.  The 2-bit path
 // copies a tile into registers first and refills its slot while it walks, so one slot per
-// warp already overlaps load and scan; the bytes path reads the raw tile throughout.
+// warp already overlaps load and scan; the bytes path reads the raw tile throughout and needs two.  The ring
+// depth is a compile-time constant of the kernels (1 / 2).
 struct LaunchShape {
 	uint32_t warps, stages, ctas;
 };
-constexpr LaunchShape kShapesPacked[] = {{32, 1, 1}, {24, 1, 1}, {16, 2, 1}, {16, 1, 1}, {12, 2, 1}, {12, 1, 1}, {8, 2, 1}, {8, 1, 1}, {4, 2, 1}, {4, 1, 1}};
+constexpr LaunchShape kShapesPacked[] = {{32, 1, 1}, {24, 1, 1}, {16, 1, 1}, {12, 1, 1}, {8, 1, 1}, {4, 1, 1}};
 constexpr LaunchShape kShapesPackedDual[] = {{16, 1, 2}, {12, 1, 2}};
 constexpr LaunchShape kShapesBytes[] = {{16, 2, 1}, {12, 2, 1}, {8, 2, 1}, {4, 2, 1}};
 

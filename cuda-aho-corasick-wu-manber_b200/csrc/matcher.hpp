@@ -68,6 +68,8 @@ struct acwm_matcher {
 	// multi-GPU count exchange (acwm_set_peers)
 	uint32_t peer_world = 0, peer_rank = 0, xepoch = 0;
 	uint64_t peer_ptrs[acwm::kMaxPeers] = {};
+	unsigned long long *d_mailbox = nullptr; // acwm_peers_create: this matcher's mailbox (owned)
+	cudaStream_t shard_stream = nullptr;     // acwm_scan_device_sharded: the stream of this matcher's device
 	double last_kernel_s = 0;
 	uint64_t last_h2d_bytes = 0; // bytes of text the last acwm_search_host sent over the link
 	int last_want_positions = 0;

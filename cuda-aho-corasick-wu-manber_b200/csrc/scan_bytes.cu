@@ -68,7 +68,7 @@ struct FrontACB : BytesKey {
 	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &, const uint8_t *, const uint32_t *, uint32_t) const {
 		return 1u;
 	}
-	__device__ __forceinline__ void init(const uint8_t *smem_tab, const uint8_t *, const ScanArgs &a) {
+	__device__ __forceinline__ void init(const uint8_t *smem_tab, const TabRef &, const ScanArgs &a) {
 		tab = IN_SMEM ? smem_tab : a.front;
 		lognc = 31 - __clz(a.prm.n_classes);
 		alpha = min(a.prm.alphabet, 255u);
@@ -129,7 +129,7 @@ struct FrontWMB : BytesKey {
 	uint32_t sh1, mult, sh2;
 	uint32_t hw[kWords];
 
-	const uint8_t *rmk;
+	TabRef rmk;
 	// offsets r < S at which some pattern holds the block ending at tile byte `pos`
 	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &a, const uint8_t *buf, const uint32_t *,
 			uint32_t pos) const {
@@ -137,9 +137,9 @@ struct FrontWMB : BytesKey {
 			return 1u;
 		const uint32_t blk = mix64(window8(buf, kHalo + pos) >> sh1);
 		const uint32_t ri = (uint32_t) (blk * a.prm.r_mult) >> a.prm.r_sh;
-		return S > 8 ? (uint32_t) reinterpret_cast<const uint16_t *>(rmk)[ri] : (uint32_t) rmk[ri];
+		return S > 8 ? rmk.u16(ri) : rmk.u8(ri);
 	}
-	__device__ __forceinline__ void init(const uint8_t *smem_tab, const uint8_t *rmask, const ScanArgs &a) {
+	__device__ __forceinline__ void init(const uint8_t *smem_tab, const TabRef &rmask, const ScanArgs &a) {
 		rmk = rmask;
 		bm = reinterpret_cast<const uint32_t *>(GLOBAL ? a.front : smem_tab);
 		sh1 = a.prm.f1_sh1;

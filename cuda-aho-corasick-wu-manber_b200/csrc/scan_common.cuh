@@ -17,6 +17,8 @@ struct Result {
 	unsigned long long global_count; // sum of `count` over the ranks of the peer exchange (== count without peers)
 	unsigned int global_epoch;   // exchange epoch global_count belongs to
 	unsigned int order_failed;   // launch number + 1 of the last scan whose position ordering gave up (never in practice)
+	unsigned int exchange_failed; // exchange epoch whose counts did not all arrive in time (a peer skipped a scan or died)
+	unsigned int pad;
 };
 
 // Working counters of the launch in flight.  kWorkRing copies: launch k uses work[k % 4] and clears
@@ -102,17 +104,31 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 	asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
-// Sum of the counts every rank left in this GPU's mailbox for exchange epoch `x` (spins until all are in).
-__device__ __forceinline__ unsigned long long collect_mailbox(const unsigned long long *box, uint32_t world, uint32_t x) {
-	unsigned long long sum = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+constexpr unsigned long long kExchangeTimeoutNs = 2000ull * 1000 * 1000; // a peer that never publishes: report, do not hang
+// Sum of the counts every rank left in this GPU's mailbox for exchange epoch `x`: spins until all are in, gives up
+// (false) after kExchangeTimeoutNs -- a peer that skipped a scan, failed before its launch or died must not hang this
+// GPU's stream for good.
+__device__ __forceinline__ bool collect_mailbox(const unsigned long long *box, uint32_t world, uint32_t x,
+		unsigned long long &sum) {
+	sum = 0;
 	const unsigned long long *slot = box + (x & (kPeerRing - 1)) * world;
+	const unsigned long long t0 = globaltimer_ns();
 	for (uint32_t r = 0; r < world; r++) {
 		unsigned long long v;
-		while (((v = ld_relaxed_sys_u64(slot + r)) >> kMailShift) != (x & 0xffffu))
+		uint32_t spins = 0;
+		while (((v = ld_relaxed_sys_u64(slot + r)) >> kMailShift) != (x & 0xffffu)) {
 			__nanosleep(32);
+			if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > kExchangeTimeoutNs)
+				return false;
+		}
 		sum += v & ((1ull << kMailShift) - 1);
 	}
-	return sum;
+	return true;
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
@@ -179,6 +195,39 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 			: "memory");
 }
 
+// A read-only table that lives in shared memory or (too large for it) in global memory: which one is a launch
+// parameter, so the access is a uniform branch between LDS and LDG instead of a generic load (64-bit address
+// arithmetic + address-space resolution on every candidate).
+struct TabRef {
+	uint32_t s;          // shared-memory address (valid when in_smem)
+	const uint8_t *g;    // global copy
+	bool in_smem;
+	__device__ __forceinline__ uint32_t u32(uint32_t word) const {
+		uint32_t v;
+		if (in_smem)
+			asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(s + 4u * word));
+		else
+			v = __ldg(reinterpret_cast<const uint32_t *>(g) + word);
+		return v;
+	}
+	__device__ __forceinline__ uint32_t u16(uint32_t i) const {
+		uint32_t v;
+		if (in_smem)
+			asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(s + 2u * i));
+		else
+			v = __ldg(reinterpret_cast<const uint16_t *>(g) + i);
+		return v;
+	}
+	__device__ __forceinline__ uint32_t u8(uint32_t i) const {
+		uint32_t v;
+		if (in_smem)
+			asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(s + i));
+		else
+			v = __ldg(g + i);
+		return v;
+	}
+};
+
 // ------------------------------------------------------------ arrival / look-back loads
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
 	unsigned long long v;
@@ -188,11 +237,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 
 // instrumentation: phase time stamps of every CTA (scripts/trace.py turns them into a timeline)
 constexpr uint32_t kTraceWords = 16 + 3 * 32; // [16 CTA phases][32 warps: first tile ready][32: scan loop done][32: tiles scanned]
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
-}
 __device__ __forceinline__ void trace_mark(const ScanArgs &a, uint32_t slot) {
 	if (a.trace)
 		a.trace[(size_t) blockIdx.x * kTraceWords + slot] = globaltimer_ns();

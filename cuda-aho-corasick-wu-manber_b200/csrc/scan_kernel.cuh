@@ -102,12 +102,13 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	uint8_t *s_warps = s_rmask + rm_bytes + f2_bytes;
 
 	const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-	const uint32_t stages = a.stages;
+	// ring depth of the per-warp tile pipeline: the 2-bit path copies a tile into registers and re-arms its ONE slot
+	// while it walks; the bytes path walks the raw tile in place and loads the next one into its second slot
+	constexpr uint32_t stages = kPacked ? 1u : 2u;
 	uint8_t *wbase = s_warps + warp * warp_smem_bytes(stages, kPk);
 	uint8_t *bufs = wbase;
 	uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + stages * kBufBytes);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + stages * kBufBytes + (kPk ? kPackWords * 4 : 0));
-	uint32_t *s_tid = reinterpret_cast<uint32_t *>(bars + kMaxStages); // span-relative tile index per ring slot
 	uint16_t *lst = reinterpret_cast<uint16_t *>(bars + 2 * kMaxStages);  // match positions of the current tile
 	unsigned long long *wlog = reinterpret_cast<unsigned long long *>(lst + kListCap); // this warp's staging reservations
 	uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_warps + W * warp_smem_bytes(stages, kPk)); // a.cnt_cap words
@@ -143,36 +144,42 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncwarp();
 
-	uint32_t tma_mask = 0, phase_mask = 0;
-	// start loading tile idx of the span (if there is one) into ring slot s
+	// Per-warp pipeline state, all in registers: slot s holds (or is receiving) tile slot_idx[s] of the span; a tile
+	// that lies inside the text arrives by ONE TMA bulk copy (slot_tma[s], its mbarrier's phase in slot_phase[s]),
+	// the first / last tiles of the text through the careful loader.
+	uint32_t slot_idx[stages], slot_tma[stages], slot_phase[stages];
+	uint8_t *slot_buf[stages];
+	uint64_t *slot_bar[stages];
+	// what a tile's copy needs, computed once: tiles [1, int_hi) lie inside the text, tile t is loaded from
+	// tile0 + t * tile_stride (load_bytes bytes: history + tile)
+	const bool packed_in = kPacked && a.packed_in;
+	const uint32_t int_hi = (uint32_t) ((packed_in ? ((a.data_hi + 63) & ~(uint64_t) 63) : (a.data_hi & ~(uint64_t) 15)) / kTile);
+	const uint32_t tile_stride = packed_in ? kTile / 4 : kTile, load_bytes = packed_in ? kLoadBytes / 4 : kLoadBytes;
+	const uint8_t *tile0 = a.text16 - (packed_in ? kHalo / 4 : kHalo);
+	const uint32_t cta_lo32 = (uint32_t) cta_lo; // tile numbers fit 28 bits (staging entries)
+	// start loading tile idx of the span (if there is one) into ring slot s.  The warp has read the slot's previous
+	// tile (into registers, or walked it) and met at a __syncwarp: the copy may overwrite it (the same write-after-
+	// read hand-over as a consumer-release / producer-acquire TMA pipeline; no proxy fence, whose MEMBAR would make
+	// lane 0 wait for all its stores in flight)
 	auto issue = [&](uint32_t s, uint32_t idx) {
-		if (lane == 0)
-			s_tid[s] = idx;
+		slot_idx[s] = idx;
 		if (idx >= n_b)
 			return;
-		const uint64_t t = cta_lo + idx;
-		uint8_t *dst = bufs + s * kBufBytes;
-		if (tile_is_interior(a, t)) {
+		const uint32_t t = cta_lo32 + idx;
+		uint8_t *dst = slot_buf[s];
+		if (t >= 1u && t < int_hi) {
 			if (lane == 0) {
-				// the generic-proxy reads of this slot are done (__syncwarp before us): order
-				// them before the async-proxy write
-				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				const uint64_t stream_pol = policy_evict_first(); // made where it is used: not two registers held across the scan
-				if (kPacked && a.packed_in) {
-					mbar_expect_tx(&bars[s], kLoadBytes / 4);
-					tma_bulk_g2s(dst, a.text16 + t * (uint64_t) (kTile / 4) - kHalo / 4, kLoadBytes / 4, &bars[s], stream_pol);
-				} else {
-					mbar_expect_tx(&bars[s], kLoadBytes);
-					tma_bulk_g2s(dst, a.text16 + t * (uint64_t) kTile - kHalo, kLoadBytes, &bars[s], stream_pol);
-				}
+				mbar_expect_tx(slot_bar[s], load_bytes);
+				tma_bulk_g2s(dst, tile0 + (uint64_t) t * tile_stride, load_bytes, slot_bar[s], stream_pol);
 			}
-			tma_mask |= 1u << s;
+			slot_tma[s] = 1;
 		} else {
-			if (kPacked && a.packed_in)
+			if (packed_in)
 				load_tile_edge_packed(a, t, dst);
 			else
 				load_tile_edge(a, t, dst);
-			tma_mask &= ~(1u << s);
+			slot_tma[s] = 0;
 		}
 	};
 	// claim the next tile of the span for ring slot s and start loading it
@@ -182,9 +189,13 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 			idx = atomicAdd(s_next, 1u);
 		issue(s, __shfl_sync(kFull, idx, 0));
 	};
-#pragma unroll 1 // cold code, once per CTA: keep it small
-	for (uint32_t s = 0; s < stages; s++)
+#pragma unroll
+	for (uint32_t s = 0; s < stages; s++) {
+		slot_phase[s] = 0;
+		slot_buf[s] = bufs + s * kBufBytes;
+		slot_bar[s] = &bars[s];
 		issue(s, s * W + warp);
+	}
 
 	// tables: global -> shared with TMA bulk copies, overlapped with the first text tiles
 	if (threadIdx.x == 0) {
@@ -236,26 +247,27 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	em.log = wlog;
 	em.n_log = em.lost = 0;
 	Front fr;
-	const uint32_t *f2 = a.prm.f2_in_smem ? s_f2 : a.filter2;
-	fr.init(s_front, a.prm.r_in_smem ? s_rmask : a.rmask, a);
+	const TabRef f2{smem_u32(s_f2), reinterpret_cast<const uint8_t *>(a.filter2), a.prm.f2_in_smem != 0};
+	fr.init(s_front, TabRef{smem_u32(s_rmask), a.rmask, a.prm.r_in_smem != 0}, a);
 
 	bool tab_ready = tab_bytes == 0; // the tables are first needed by walk(): the first tile is loaded and packed under their copy
-	for (uint32_t slot = 0;; slot = slot + 1 == stages ? 0 : slot + 1) {
-		const uint32_t idx = s_tid[slot];
+	for (;;) {
+		// the oldest slot is slot 0 (the bytes path rotates its two slots at the end of the iteration)
+		const uint32_t idx = slot_idx[0];
 		if (idx >= n_b)
 			break; // the span is exhausted (claims are handed out in ascending order)
 		const uint64_t tile = cta_lo + idx;
-		if ((tma_mask >> slot) & 1u) {
-			mbar_wait(&bars[slot], (phase_mask >> slot) & 1u);
-			phase_mask ^= 1u << slot;
+		if (slot_tma[0]) {
+			mbar_wait(slot_bar[0], slot_phase[0]);
+			slot_phase[0] ^= 1u;
 		}
 		__syncwarp();
 
-		const uint8_t *buf = bufs + slot * kBufBytes;
+		const uint8_t *buf = slot_buf[0];
 		fr.load(a, buf, pk, badacc);
 		if constexpr (kPacked) { // the tile now lives in registers (+ pk): refill the slot while we walk
 			__syncwarp();
-			refill(slot);
+			refill(0);
 		}
 		if (!tab_ready) {
 			if (lane == 0)
@@ -283,13 +295,28 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 				fr.mask_range(lo_s, hi_s);
 			}
 			const uint32_t cnt = fr.count();
-			if (__any_sync(kFull, cnt != 0)) {
-				const uint32_t incl = warp_incl_scan(cnt);
-				total = __shfl_sync(kFull, incl, 31);
+			const uint32_t b1 = __ballot_sync(kFull, cnt != 0);
+			if (b1) {
+				// rank of a lane's first match = matches of the lanes in front of it.  The usual tile of a sparse text has
+				// at most two matches per lane: two ballots give the prefix (cnt = [cnt >= 1] + [cnt >= 2]) and every lane
+				// stages its own matches; dense tiles take the shuffle scan and leave through the shared list
+				// (full-warp stores).
+				const uint32_t b2 = __ballot_sync(kFull, cnt > 1);
+				const bool sparse = __ballot_sync(kFull, cnt > 2) == 0;
+				uint32_t k;
+				if (sparse) {
+					uint32_t lt;
+					asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+					k = __popc(b1 & lt) + __popc(b2 & lt);
+					total = __popc(b1) + __popc(b2);
+				} else {
+					const uint32_t incl = warp_incl_scan(cnt);
+					total = __shfl_sync(kFull, incl, 31);
+					k = incl - cnt;
+				}
 				if (a.want_positions) {
 					em.reserve(total);
-					uint32_t k = incl - cnt;
-					if (total <= kListCap) { // the usual case: positions -> shared list, then full-warp stores
+					if (!sparse && total <= kListCap) { // positions -> shared list, then full-warp stores
 #pragma unroll
 						for (int g = 0; g < Front::kWords; g++)
 							for (uint32_t w = fr.hw[g]; w; w &= w - 1)
@@ -326,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 			auto check_end = [&](uint32_t tp) -> uint32_t {
 				const uint32_t key = Front::key_at(a, buf, pk, tp);
 				const uint32_t i2 = (uint32_t) (key * a.prm.f2_mult) >> a.prm.f2_sh;
-				if ((f2[i2 >> 5] >> (i2 & 31)) & 1u)
+				if ((f2.u32(i2 >> 5) >> (i2 & 31)) & 1u)
 					return verify_window(a, key, tile_start + tp);
 				return 0u;
 			};
@@ -443,8 +470,16 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 		}
 		em.end_tile(total);
 		__syncwarp(); // every lane is done with this slot (and pk) before it is refilled / rewritten
-		if constexpr (!kPacked)
-			refill(slot);
+		if constexpr (!kPacked) { // refill the slot just walked, then the other slot (loaded meanwhile) becomes slot 0
+			refill(0);
+			const uint32_t ti = slot_idx[0], tt = slot_tma[0], tp = slot_phase[0];
+			uint8_t *tb = slot_buf[0];
+			uint64_t *tr = slot_bar[0];
+			slot_idx[0] = slot_idx[stages - 1], slot_tma[0] = slot_tma[stages - 1], slot_phase[0] = slot_phase[stages - 1];
+			slot_buf[0] = slot_buf[stages - 1], slot_bar[0] = slot_bar[stages - 1];
+			slot_idx[stages - 1] = ti, slot_tma[stages - 1] = tt, slot_phase[stages - 1] = tp;
+			slot_buf[stages - 1] = tb, slot_bar[stages - 1] = tr;
+		}
 	}
 	if (a.trace && lane == 0)
 		trace_mark(a, 48 + warp);
@@ -508,8 +543,12 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	auto collect_peers = [&]() {
 		if (a.xepoch < 2)
 			return;
-		a.ctl->result.global_count = collect_mailbox(a.peers[a.rank], a.world, a.xepoch - 1);
-		a.ctl->result.global_epoch = a.xepoch - 1;
+		unsigned long long sum;
+		if (collect_mailbox(a.peers[a.rank], a.world, a.xepoch - 1, sum)) {
+			a.ctl->result.global_count = sum;
+			a.ctl->result.global_epoch = a.xepoch - 1;
+		} else
+			a.ctl->result.exchange_failed = a.xepoch - 1;
 	};
 	const unsigned long long tag = (unsigned long long) ((a.epoch + 1u) & 0xffffffu) << kTotalShift;
 	if (threadIdx.x == 0) {

@@ -5,8 +5,10 @@
 // registers, 16 symbols -> one 32-bit word (4 IMAD + 3 PRMT), so the walk below runs on
 // 8 registers per lane:
 //   AC<K>  dense DFA with the failure function folded in, K symbols per shared-memory
-//          lookup (uint16 entry = byte offset of the next row | K hit bits).  Supersedes the
-//          one-symbol goto/failure walk of cuda/cuda_ac.cu:88-95.
+//          lookup (uint16 entry = byte offset of the next row | K hit bits << 1, bit 0 clear: the
+//          hit bits sit where the next lookup's symbols go, so the address of the next lookup is ONE
+//          bitwise select of entry and text).  Supersedes the one-symbol goto/failure walk of
+//          cuda/cuda_ac.cu:88-95.
 //   WM<S>  Wu-Manber block filter sampled every S symbols (SHIFT[block] < S as a
 //          bitmap).  Supersedes the divergent skip loop of cuda/cuda_wm.cu:136-176.
 // Once the chunk is in registers the warp refills its raw slot (TMA) and walks; one slot
@@ -87,12 +89,12 @@ struct FrontAC : PackedKey {
 	static constexpr int kSS = GLOBAL ? 2 : 1;                  // log2(entry bytes): symbols sit above it in the address
 	static constexpr int kOff = (K - (int) kLane % K) % K;      // 2 / 0 / 0
 	static constexpr int kStrides = ((int) kLane + kOff) / K;   // 38 / 56 / 112
-	static constexpr int kGroup = (K == 3) ? 10 : 32 / K;       // strides per hit word
-	static constexpr int kGroupSyms = kGroup * K;               // 30 / 32 / 32
+	static constexpr int kGroup = (32 - kSS) / K;               // strides per hit word: 10 / 15 / 31 (global: 15 / 30)
+	static constexpr int kGroupSyms = kGroup * K;               // 30 / 30 / 31
 	static constexpr int kWords = (kStrides + kGroup - 1) / kGroup; // 4
 	static constexpr uint32_t kSymMask2 = ((1u << (2 * K)) - 1) << kSS;
-	static constexpr uint32_t kRowMask = ~((1u << (2 * K + kSS)) - 1);
-	static constexpr uint32_t kHitMask = (1u << K) - 1;
+	static constexpr uint32_t kHitMask = ((1u << K) - 1) << kSS; // in the entry, above its kSS clear bits
+	static_assert(K * kGroup + kSS <= 32, "the hit word keeps the entry's kSS low bits clear");
 	static constexpr int kExpand = 1; // probes per candidate
 
 	const uint8_t *tab; // shared-memory DFA
@@ -103,7 +105,7 @@ struct FrontAC : PackedKey {
 	uint32_t H[3];      // long warm-up only: symbols -64..-17
 	uint32_t hw[kWords];
 
-	__device__ __forceinline__ void init(const uint8_t *table, const uint8_t *, const ScanArgs &a) {
+	__device__ __forceinline__ void init(const uint8_t *table, const TabRef &, const ScanArgs &a) {
 		tab = GLOBAL ? a.front : table;
 		// the state must have seen depth-1 symbols of history when the chunk starts; the first
 		// in-chunk stride covers kOff of them
@@ -112,35 +114,39 @@ struct FrontAC : PackedKey {
 		nwu = need > (uint32_t) kOff ? (need - kOff + K - 1) / K : 0u;
 		hist = kOff + K * nwu; // <= 16: W[0] is enough; else up to 64 symbols of raw history
 	}
-	static __device__ __forceinline__ uint32_t sym_of(int g, int b) { return (uint32_t) (g * kGroupSyms + b - kOff); }
+	// bit b of hit word g (b >= kSS: the words keep the entries' low clear bits) = a hit at this chunk symbol
+	static __device__ __forceinline__ uint32_t sym_of(int g, int b) { return (uint32_t) (g * kGroupSyms + b - kSS - kOff); }
 	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &, const uint8_t *, const uint32_t *, uint32_t) const {
 		return 1u; // a hit of the truncated automaton is probed where it ends
 	}
 
-	__device__ __forceinline__ uint32_t step_of(uint32_t &e, uint32_t sym2) const {
-		const uint32_t addr = (e & kRowMask) | sym2; // one LOP3 between two dependent lookups
+	// x = text bits with the stride's K symbols at bits [kSS, kSS + 2K) (anything elsewhere).  The entry keeps its row
+	// offset above those bits, its hit bits inside them and zeros below: the next address is a bitwise select
+	// (one LOP3 between two dependent lookups).  Returns the entry's hit bits, in place.
+	__device__ __forceinline__ uint32_t step_of(uint32_t &e, uint32_t x) const {
+		const uint32_t addr = (e & ~kSymMask2) | (x & kSymMask2);
 		if (GLOBAL)
 			e = __ldg(reinterpret_cast<const uint32_t *>(tab + addr));
 		else
 			e = *reinterpret_cast<const uint16_t *>(tab + addr);
 		return e & kHitMask;
 	}
-	__device__ __forceinline__ uint32_t step(uint32_t sym2) { return step_of(ent, sym2); }
-	// symbols of in-chunk stride i, already shifted to their place in the entry address
+	__device__ __forceinline__ uint32_t step(uint32_t x) { return step_of(ent, x); }
+	// text bits of in-chunk stride i with its symbols at [kSS, kSS + 2K) (not masked)
 	template <int I>
 	__device__ __forceinline__ uint32_t sym_at() const {
 		constexpr int bit = 32 - 2 * kOff + 2 * K * I; // W[0] holds stream bits 0..31, chunk symbol c sits at bit 32 + 2c
 		constexpr int wi = bit >> 5, sh = bit & 31;
 		if constexpr (sh + 2 * K <= 32)
-			return (sh >= kSS ? (W[wi] >> (sh >= kSS ? sh - kSS : 0)) : (W[wi] << (sh < kSS ? kSS - sh : 0))) & kSymMask2;
+			return sh >= kSS ? (W[wi] >> (sh >= kSS ? sh - kSS : 0)) : (W[wi] << (sh < kSS ? kSS - sh : 0));
 		else // only K = 3 straddles words, and K = 3 tables are never global
-			return __funnelshift_r(W[wi], W[wi + 1], sh - 1) & kSymMask2;
+			return __funnelshift_r(W[wi], W[wi + 1], sh - 1);
 	}
 	template <int I>
 	__device__ __forceinline__ void stride(uint32_t &e) {
 		uint32_t h = step_of(e, sym_at<I>());
 		if (I == 0 && kOff)
-			h &= ~((1u << kOff) - 1); // symbols in front of the chunk belong to the previous lane
+			h &= ~(((1u << kOff) - 1) << kSS); // symbols in front of the chunk belong to the previous lane
 		hw[I / kGroup] += h << (K * (I % kGroup));
 	}
 	template <int J, int HALF>
@@ -237,10 +243,10 @@ struct FrontAC : PackedKey {
 		return c;
 	}
 	__device__ __forceinline__ void mask_range(uint32_t lo_sym, uint32_t hi_sym) {
-		// keep only chunk-relative symbols in [lo_sym, hi_sym); bit b of word g is symbol g*kGroupSyms + b - kOff
+		// keep only chunk-relative symbols in [lo_sym, hi_sym); bit b of word g is symbol g*kGroupSyms + b - kSS - kOff
 #pragma unroll
 		for (int g = 0; g < kWords; g++) {
-			const int base = g * kGroupSyms - kOff;
+			const int base = g * kGroupSyms - kOff - kSS;
 			const int lo = max((int) lo_sym - base, 0), hi = min((int) hi_sym - base, 32);
 			uint32_t keep = 0;
 			if (hi > lo)
@@ -260,12 +266,12 @@ struct FrontWM : PackedKey {
 	static constexpr int kExpand = S;
 
 	const uint32_t *bm; // shared-memory block bitmap
-	const uint8_t *rmk; // shared-memory offset masks
+	TabRef rmk;         // offset masks
 	uint32_t sh1, mult, sh2;
 	uint32_t W[8];
 	uint32_t hw[kWords];
 
-	__device__ __forceinline__ void init(const uint8_t *table, const uint8_t *rmask, const ScanArgs &a) {
+	__device__ __forceinline__ void init(const uint8_t *table, const TabRef &rmask, const ScanArgs &a) {
 		bm = reinterpret_cast<const uint32_t *>(MODE == 2 ? a.front : table);
 		rmk = rmask;
 		sh1 = a.prm.f1_sh1;
@@ -281,7 +287,7 @@ struct FrontWM : PackedKey {
 			return 1u;
 		const uint32_t blk = window16(pk, pos) >> sh1;
 		const uint32_t ri = (uint32_t) (blk * a.prm.r_mult) >> a.prm.r_sh;
-		return S > 8 ? (uint32_t) reinterpret_cast<const uint16_t *>(rmk)[ri] : (uint32_t) rmk[ri];
+		return S > 8 ? rmk.u16(ri) : rmk.u8(ri);
 	}
 
 	__device__ __forceinline__ void load(const ScanArgs &a, const uint8_t *buf, uint32_t *pk, uint32_t &badacc) {

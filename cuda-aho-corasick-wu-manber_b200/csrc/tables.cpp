@@ -391,11 +391,13 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 				hits |= (e & 1) << i;
 				st = e >> 1;
 			}
+			// the hit bits sit above the entry's log2(entry bytes) clear low bits, i.e. where the symbols of the next
+			// lookup go: the kernel forms the next address with one bitwise select (scan_packed.cu, FrontAC::step_of)
 			if (global)
-				reinterpret_cast<uint32_t *>(c.front.data())[(size_t) r * cols + idx] = (st * cols * 4) | hits;
+				reinterpret_cast<uint32_t *>(c.front.data())[(size_t) r * cols + idx] = (st * cols * 4) | (hits << 2);
 			else
 				reinterpret_cast<uint16_t *>(c.front.data())[(size_t) r * cols + idx] =
-						(uint16_t) ((st << (2 * K + 1)) | hits);
+						(uint16_t) ((st << (2 * K + 1)) | (hits << 1));
 		}
 	prm.stride = K;
 	prm.depth = bestD;
@@ -714,7 +716,7 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 		const bool ok = (want.warps == 32 || want.warps == 24 || want.warps == 16 || want.warps == 12 || want.warps == 8
 								|| want.warps == 4)
 				&& want.warps * 32 == (opts.force_threads ? opts.force_threads : want.warps * 32)
-				&& want.stages >= (packed ? 1u : 2u) && want.stages <= kMaxStages
+				&& want.stages == (packed ? 1u : 2u) // the ring depth is a compile-time constant of the kernels
 				&& (want.ctas == 1 || (packed && (want.warps == 16 || want.warps == 12)))
 				&& shape_fits(smem_tables16(out), want, pk_copy);
 		if (!ok) {

@@ -219,6 +219,28 @@ int acwm_device_count(void);
 int acwm_search_host_sharded(acwm_matcher *const *mts, uint32_t world, const uint8_t *text, uint64_t n, uint64_t *count,
 		uint64_t *positions, uint64_t cap, uint64_t *n_written, uint64_t *shard_counts);
 
+/* The same multi-rank flow for DEVICE-RESIDENT text, in one process, without torch, NCCL or MPI: what replaces
+ * MPI_Scatterv + MPI_Reduce (main.c:488,656) when the shards already sit in HBM.  mts[r] (uploaded, one per shard;
+ * several may share a device) gets a zero-initialised mailbox in its device's memory (cudaMalloc), peer access is
+ * enabled between the devices involved (cudaDeviceEnablePeerAccess) and the matchers are wired with acwm_set_peers:
+ * from then on every acwm_scan_device_sharded exchanges the per-shard counts INSIDE the scan kernels over NVLink.
+ * ACWM_ERR_UNSUPPORTED if two of the devices cannot access each other's memory. */
+int acwm_peers_create(acwm_matcher *const *mts, uint32_t world);
+int acwm_peers_destroy(acwm_matcher *const *mts, uint32_t world);
+/* One scan of every shard: d_shards[r] (on mts[r]'s device) holds shard r of the text INCLUDING its halo, shard_lens[r]
+ * bytes (acwm_shard_bounds); shard r > 0 reports ends from m_max-1 on, so every match is reported exactly once.
+ * Asynchronous; matchers of one device run on one stream, in rank order.  Like a collective, every call scans all
+ * shards.  acwm_fetch_sharded waits for the last one and returns the count summed over the shards as the kernels
+ * exchanged it (every shard's kernel holds the same sum) and the per-shard counts; positions stay per shard
+ * (acwm_fetch on mts[r], shard-local, + the shard start = global). */
+int acwm_scan_device_sharded(acwm_matcher *const *mts, uint32_t world, const uint8_t *const *d_shards,
+		const uint64_t *shard_lens, int want_positions);
+int acwm_fetch_sharded(acwm_matcher *const *mts, uint32_t world, uint64_t *global_count, uint64_t *shard_counts);
+/* Device buffers for callers that are plain C (no CUDA runtime of their own): a copy of n host bytes in the memory
+ * of `device`, and its release. */
+int acwm_text_to_device(int device, const uint8_t *text, uint64_t n, uint8_t **d_text);
+void acwm_device_free(int device, void *d_ptr);
+
 /* Raw views of the compiled tables (tests and diagnostics).  `which` is one of the
  * ACWM_BLOB_* ids; returns ACWM_ERR_INVALID if this matcher has no such table. */
 enum {

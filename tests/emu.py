@@ -96,7 +96,7 @@ class Emulator:
         return out
 
     # ------------------------------------------------------------ front ends
-    def _ac_hits(self, sym, chunk, K_bits, cols_of, row_shift):
+    def _ac_hits(self, sym, chunk, K_bits, cols_of, row_shift, hit_shift=0):
         """Generic chunked DFA walk; returns sorted hit positions (may include e >= n).
         Mirrors FrontAC::scan / FrontACB::scan: the in-chunk strides start `off` symbols in
         front of the chunk so that they end exactly at the chunk end, preceded by the
@@ -126,7 +126,8 @@ class Emulator:
                 idx |= ext[starts + hist + first + i] << (K_bits * i)
             ent = tab[state * cols + idx]
             state = ent >> row_shift
-            h = ent & ((1 << K) - 1)
+            # packed DFA entries keep the K hit bits above log2(entry bytes) clear low bits; bytes path: bit 0
+            h = (ent >> hit_shift) & ((1 << K) - 1)
             if t >= 0 and h.any():
                 for i in range(K):
                     if first + i < 0:
@@ -164,8 +165,8 @@ class Emulator:
             win = self._win16(text)
             if p.algo == acwm.AC and not p.front_kind:
                 # entry = byte offset of the next row | hits (uint16 in shared memory, uint32 in global memory)
-                hits = self._ac_hits(sym, 112, 2, 1 << (2 * p.stride),
-                                     2 * p.stride + (1 if self.info["table_in_smem"] else 2))
+                ss = 1 if self.info["table_in_smem"] else 2
+                hits = self._ac_hits(sym, 112, 2, 1 << (2 * p.stride), 2 * p.stride + ss, ss)
                 hits = hits[(hits >= m_min - 1) & (hits < n)]
                 if p.exact_front:
                     return int(hits.size), hits.astype(np.uint64)

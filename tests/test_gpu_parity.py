@@ -66,8 +66,8 @@ def test_empty_text(acwm, torch_cuda):
     assert count == 0 and pos.size == 0
 
 
-@pytest.mark.parametrize("threads,stages", [(128, 2), (256, 3), (384, 2), (512, 2), (256, 4), (768, 1), (1024, 1),
-                                            (512, 1)])
+@pytest.mark.parametrize("threads,stages", [(128, 1), (256, 1), (384, 1), (512, 1), (768, 1), (1024, 1),
+                                            (128, 2), (256, 2), (384, 2), (512, 2)])
 def test_launch_shape_variants(acwm, oracle, torch_cuda, threads, stages):
     """Every (warps, ring depth) shape of the scan kernel gives the same matches."""
     for cname in ("c1_ac_dna_p100_m8", "c2_wm_dna_p1000_m16", "ac_dna_depth5", "wm_ascii_p1000_m8",
@@ -75,8 +75,8 @@ def test_launch_shape_variants(acwm, oracle, torch_cuda, threads, stages):
         case = next(c for c in RANDOM_CASES if c[0] == cname)
         name, algo, alphabet, p, m, n, opts = case
         pats, text = make_case(case)
-        if alphabet > 4 and (stages < 2 or threads > 512):
-            continue  # the bytes path reads the raw tile while it walks: >= 2 slots, <= 16 warps
+        if (alphabet > 4) != (stages == 2) or (alphabet > 4 and threads > 512):
+            continue  # 2-bit path: one slot per warp; bytes path (walks the raw tile): two slots, <= 16 warps
         try:
             acwm.Matcher(algo, pats, alphabet, force_threads=threads, force_stages=stages, **opts).close()
         except acwm.AcwmError as e:
@@ -472,6 +472,47 @@ def test_baseline_configs_full_size(acwm, oracle, have_ref, torch_cuda):
         assert c3 == count and np.array_equal(p3, pos)
         mt.close()
         other.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_device_sharded_count_exchange_c_abi(acwm, oracle, torch_cuda, world):
+    """acwm_peers_create + acwm_scan_device_sharded + acwm_fetch_sharded: the multi-rank flow for device-resident shards
+    in one process through the C ABI alone.  The per-shard counts cross between the matchers through the mailboxes
+    the scan kernels write (peer-mapped over NVLink when the shards sit on several GPUs; on a one-GPU box every
+    matcher lives on GPU 0, which still runs acwm_set_peers, the in-kernel publish and the collect): the exchanged sum,
+    the per-shard counts and every position equal the oracle's, over several rounds of back-to-back scans."""
+    torch = torch_cuda
+    n_dev = acwm.device_count()
+    for cname in ("c1_ac_dna_p100_m8", "c2_wm_dna_p1000_m16", "c4_wm_ascii_mixed_8_64"):
+        case = next(c for c in RANDOM_CASES if c[0] == cname)
+        name, algo, alphabet, p, m, n, opts = case
+        pats, text = make_case(case)
+        texts = [text, np.roll(text, 12345)]
+        refs = [oracle.set_search(pats, t) for t in texts]
+        m_max = max(q.size for q in pats) if isinstance(pats, list) else pats.shape[1]
+        mts = [acwm.Matcher(algo, pats, alphabet, **opts).upload(device=r % n_dev, pos_capacity=text.size) for r in range(world)]
+        acwm.peers_create(mts)
+        bounds = [acwm.shard_bounds(text.size, world, r, m_max - 1) for r in range(world)]
+        shards = [[torch.from_numpy(t[s:s + l]).to(f"cuda:{r % n_dev}") for r, (s, l) in enumerate(bounds)] for t in texts]
+        for rounds in (1, 3):
+            for last in (0, 1):
+                for k in range(rounds):  # back-to-back collective scans, no host synchronisation in between
+                    acwm.scan_device_sharded(mts, shards[(last + k + 1) % 2])
+                acwm.scan_device_sharded(mts, shards[last])
+                g, per = acwm.fetch_sharded(mts)
+                ref = refs[last]
+                assert g == ref["count"] == int(per.sum()), (cname, world, rounds, last)
+                got = []
+                for r, (start, length) in enumerate(bounds):
+                    torch.cuda.set_device(r % n_dev)
+                    c, pos, _ = mts[r].fetch(cap=text.size)
+                    assert c == int(per[r]) == pos.size
+                    got.append(pos + np.uint64(start))
+                assert np.array_equal(np.concatenate(got), ref["positions"]), (cname, world, rounds, last)
+        acwm.peers_destroy(mts)
+        torch.cuda.set_device(0)
+        for mt in mts:
+            mt.close()
 
 
 def _planted(torch, d_text, pats, ends):
