@@ -180,7 +180,7 @@ static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
 static uint32_t kernel_tune() {
 	static const uint32_t v = [] {
 		const char *e = getenv("ACWM_TUNE");
-		return e && *e ? (uint32_t) strtoul(e, nullptr, 0) : kTuneCoopVerify;
+		return e && *e ? (uint32_t) strtoul(e, nullptr, 0) : (kTuneCoopVerify | (kTuneLaneLocalDefault << 8));
 	}();
 	return v;
 }
@@ -222,6 +222,7 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	a.want_positions = want_positions;
 	a.append = append;
 	a.tune = kernel_tune();
+	a.lane_local = (a.tune & kTuneCoopVerify) ? ((a.tune >> 8) & 0xffu) : kListCap;
 	a.packed_in = packed_in ? 1u : 0u;
 	a.trace = mt->d_trace;
 	if (exchange && mt->peer_world > 1) {
@@ -251,6 +252,20 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	const uint32_t smem_max = dual ? kMaxSmemDual : kMaxSmem;
 	a.cnt_cap = (uint32_t) std::min<uint64_t>(a.tiles_per_cta, (smem_max - c.info.smem_bytes) / 4);
 	const uint32_t smem = c.info.smem_bytes + a.cnt_cap * 4;
+	{ // the shared-memory layout of scan_kernel.cuh: [1 KiB][per-warp areas][front][offset masks][stage-2 bitmap][per-tile counts]
+		const bool exact = c.prm.algo == ACWM_ALGO_AC && !c.prm.front_kind && c.prm.exact_front;
+		const bool pk_copy = c.prm.packed2bit && !exact;
+		const uint32_t stages = c.prm.packed2bit ? 1u : 2u;
+		const uint32_t front = a.front_in_smem ? ((a.front_bytes + 15u) & ~15u) : 0u;
+		const uint32_t rm = (exact || !c.prm.r_in_smem) ? 0u : ((c.prm.r_entries * c.prm.r_entry_bytes + 15u) & ~15u);
+		const uint32_t f2 = (exact || !c.prm.f2_in_smem) ? 0u : ((c.prm.f2_words * 4u + 15u) & ~15u);
+		a.s_rmask = kDynSmemBase + kSmemReserve + warps * warp_smem_bytes(stages, pk_copy) + front;
+		a.s_f2 = a.s_rmask + rm;
+		a.s_cnt = a.s_f2 + f2;
+		if (a.s_cnt - kDynSmemBase + a.cnt_cap * 4 > smem) {
+			return set_error(ACWM_ERR_INVALID, "scan kernel: shared-memory layout exceeds the launch size");
+		}
+	}
 	const bool two_at_most = 3 * (smem + 1024) > kSmemPerSmTotal; // CTAs of this kernel per SM
 	a.pdl = (chain && grid == sms && two_at_most) ? 1 : 0;
 	if (grid > 256)

@@ -16,12 +16,12 @@
 
 namespace acwm {
 
-// 64-bit window of the 8 bytes ending at buffer byte index bidx (>= 7).
-__device__ __forceinline__ uint64_t window8(const uint8_t *buf, uint32_t bidx) {
+// 64-bit window of the 8 bytes ending at buffer byte index bidx (>= 7); buf = shared address of the slot.
+__device__ __forceinline__ uint64_t window8(uint32_t buf, uint32_t bidx) {
 	const uint32_t b0 = bidx - 7;
-	const uint32_t *w = reinterpret_cast<const uint32_t *>(buf) + (b0 >> 2);
+	const uint32_t w = buf + (b0 & ~3u);
 	const uint32_t sh = (b0 & 3) * 8;
-	const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+	const uint32_t w0 = lds32(w), w1 = lds32(w + 4), w2 = lds32(w + 8);
 	const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
 	return ((uint64_t) hi << 32) | lo;
 }
@@ -32,8 +32,7 @@ __device__ __forceinline__ uint32_t mix64(uint64_t v) {
 
 struct BytesKey {
 	static constexpr bool kPacked = false;
-	static __device__ __forceinline__ uint32_t key_at(const ScanArgs &a, const uint8_t *buf, const uint32_t *,
-			uint32_t pos) {
+	static __device__ __forceinline__ uint32_t key_at(const ScanArgs &a, uint32_t buf, uint32_t, uint32_t pos) {
 		return mix64(window8(buf, kHalo + pos) >> (64 - 8 * a.prm.b2));
 	}
 };
@@ -41,19 +40,20 @@ struct BytesKey {
 // one lane's 112-byte chunk: 7 groups of 16 bytes, each handed to the front end together
 // with the 16 bytes in front of it
 #define ACWM_SCAN_GROUPS()                                         \
-	const uint8_t *chunk;                                          \
-	__device__ __forceinline__ void load(const ScanArgs &, const uint8_t *buf, uint32_t *, uint32_t &) { chunk = buf + kHalo + lane_id() * kLane; } \
+	uint32_t chunk;                                                \
+	__device__ __forceinline__ void load(const ScanArgs &, uint32_t buf, uint32_t, uint32_t &) { chunk = buf + kHalo + lane_id() * kLane; } \
 	__device__ __forceinline__ void walk(const ScanArgs &a) {      \
 		begin(a, chunk);                                           \
-		uint4 prev = *reinterpret_cast<const uint4 *>(chunk - 16); \
+		uint4 prev = lds128(chunk - 16);                           \
 		uint4 c;                                                   \
-		c = *reinterpret_cast<const uint4 *>(chunk + 0);  group<0>(prev, c); prev = c; \
-		c = *reinterpret_cast<const uint4 *>(chunk + 16); group<1>(prev, c); prev = c; \
-		c = *reinterpret_cast<const uint4 *>(chunk + 32); group<2>(prev, c); prev = c; \
-		c = *reinterpret_cast<const uint4 *>(chunk + 48); group<3>(prev, c); prev = c; \
-		c = *reinterpret_cast<const uint4 *>(chunk + 64); group<4>(prev, c); prev = c; \
-		c = *reinterpret_cast<const uint4 *>(chunk + 80); group<5>(prev, c); prev = c; \
-		c = *reinterpret_cast<const uint4 *>(chunk + 96); group<6>(prev, c);           \
+		c = lds128(chunk + 0);  group<0>(prev, c); prev = c;       \
+		c = lds128(chunk + 16); group<1>(prev, c); prev = c;       \
+		c = lds128(chunk + 32); group<2>(prev, c); prev = c;       \
+		c = lds128(chunk + 48); group<3>(prev, c); prev = c;       \
+		c = lds128(chunk + 64); group<4>(prev, c); prev = c;       \
+		c = lds128(chunk + 80); group<5>(prev, c); prev = c;       \
+		c = lds128(chunk + 96); group<6>(prev, c);                 \
+		finish_words();                                            \
 	}
 
 // ------------------------------------------------------------ front end: AC over bytes
@@ -61,15 +61,17 @@ template <bool IN_SMEM>
 struct FrontACB : BytesKey {
 	static constexpr int kWords = 4; // 112 hit bits
 	static constexpr int kExpand = 1;
-	const uint8_t *tab;
+	uint32_t tab_s;     // shared-memory automaton (shared address)
+	const uint8_t *tab; // global-memory automaton
 	uint32_t ent, lognc, alpha;
 	uint32_t hw[kWords];
 
-	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &, const uint8_t *, const uint32_t *, uint32_t) const {
+	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &, uint32_t, uint32_t, uint32_t) const {
 		return 1u;
 	}
-	__device__ __forceinline__ void init(const uint8_t *smem_tab, const TabRef &, const ScanArgs &a) {
-		tab = IN_SMEM ? smem_tab : a.front;
+	__device__ __forceinline__ void init(uint32_t smem_tab, const TabRef &, const ScanArgs &a) {
+		tab_s = smem_tab;
+		tab = a.front;
 		lognc = 31 - __clz(a.prm.n_classes);
 		alpha = min(a.prm.alphabet, 255u);
 	}
@@ -79,19 +81,20 @@ struct FrontACB : BytesKey {
 		const uint32_t cls = min(byte, alpha);
 		const uint32_t idx = ((ent >> 1) << lognc) + cls;
 		if (IN_SMEM)
-			ent = reinterpret_cast<const uint16_t *>(tab)[idx];
+			ent = lds_u16(tab_s + 2 * idx);
 		else
 			ent = __ldg(reinterpret_cast<const uint32_t *>(tab) + idx);
 		return ent & 1u;
 	}
-	__device__ __forceinline__ void begin(const ScanArgs &a, const uint8_t *chunk) {
+	__device__ __forceinline__ void begin(const ScanArgs &a, uint32_t chunk) {
 		ent = 0;
 #pragma unroll
 		for (int g = 0; g < kWords; g++)
 			hw[g] = 0;
 		const uint32_t nwu = a.prm.depth - 1;
+#pragma unroll 1
 		for (uint32_t i = 0; i < nwu; i++)
-			(void) step(chunk[(int) i - (int) nwu]);
+			(void) step(lds_u8(chunk + i - nwu));
 	}
 	// one 16-byte group: G = group index 0..6
 	template <int G>
@@ -103,6 +106,7 @@ struct FrontACB : BytesKey {
 			hw[(G * 16 + k) / 32] += h << ((G * 16 + k) % 32);
 		}
 	}
+	__device__ __forceinline__ void finish_words() {}
 	ACWM_SCAN_GROUPS()
 	__device__ __forceinline__ uint32_t count() const {
 		return __popc(hw[0]) + __popc(hw[1]) + __popc(hw[2]) + __popc(hw[3]);
@@ -125,32 +129,38 @@ struct FrontWMB : BytesKey {
 	static constexpr int kSamples = (int) kLane / S; // 112 / 56 / 28 / 14 / 7
 	static constexpr int kWords = (kSamples + 31) / 32;
 	static constexpr int kExpand = S;
-	const uint32_t *bm;
+	uint32_t bm_s;      // shared-memory block bitmap (shared address)
+	const uint32_t *bm; // global-memory block bitmap
 	uint32_t sh1, mult, sh2;
 	uint32_t hw[kWords];
 
 	TabRef rmk;
 	// offsets r < S at which some pattern holds the block ending at tile byte `pos`
-	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &a, const uint8_t *buf, const uint32_t *,
-			uint32_t pos) const {
+	__device__ __forceinline__ uint32_t probe_mask(const ScanArgs &a, uint32_t buf, uint32_t, uint32_t pos) const {
 		if (S == 1)
 			return 1u;
 		const uint32_t blk = mix64(window8(buf, kHalo + pos) >> sh1);
 		const uint32_t ri = (uint32_t) (blk * a.prm.r_mult) >> a.prm.r_sh;
 		return S > 8 ? rmk.u16(ri) : rmk.u8(ri);
 	}
-	__device__ __forceinline__ void init(const uint8_t *smem_tab, const TabRef &rmask, const ScanArgs &a) {
+	__device__ __forceinline__ void init(uint32_t smem_tab, const TabRef &rmask, const ScanArgs &a) {
 		rmk = rmask;
-		bm = reinterpret_cast<const uint32_t *>(GLOBAL ? a.front : smem_tab);
+		bm_s = smem_tab;
+		bm = reinterpret_cast<const uint32_t *>(a.front);
 		sh1 = a.prm.f1_sh1;
 		mult = a.prm.f1_mult;
 		sh2 = a.prm.f1_sh2;
 	}
 	static __device__ __forceinline__ uint32_t sym_of(int g, int b) { return (uint32_t) ((g * 32 + b) * S); }
-	__device__ __forceinline__ void begin(const ScanArgs &, const uint8_t *) {
+	__device__ __forceinline__ void begin(const ScanArgs &, uint32_t) {
 #pragma unroll
 		for (int g = 0; g < kWords; g++)
 			hw[g] = 0;
+	}
+	__device__ __forceinline__ void finish_words() {
+		constexpr int r = kSamples % 32; // the last word holds fewer than 32 samples: bring them down to bit 0
+		if constexpr (r != 0)
+			hw[kWords - 1] >>= 32 - r;
 	}
 	template <int G>
 	__device__ __forceinline__ void group(const uint4 &p, const uint4 &c) {
@@ -166,8 +176,8 @@ struct FrontWMB : BytesKey {
 			const uint32_t hi = (bh & 3) ? __byte_perm(X[bh >> 2], X[(bh >> 2) + 1], 0x3210 + 0x1111 * (bh & 3)) : X[bh >> 2];
 			const uint64_t blk = (((uint64_t) hi << 32) | lo) >> sh1;
 			const uint32_t idx = (uint32_t) (mix64(blk) * mult) >> sh2;
-			const uint32_t word = GLOBAL ? __ldg(bm + (idx >> 5)) : bm[idx >> 5];
-			hw[j / 32] += ((word >> (idx & 31)) & 1u) << (j % 32);
+			const uint32_t word = GLOBAL ? __ldg(bm + (idx >> 5)) : lds32(bm_s + ((idx >> 3) & ~3u));
+			hw[j / 32] = __funnelshift_r(hw[j / 32], word >> (idx & 31), 1); // the sample's bit enters from the top
 		}
 	}
 	ACWM_SCAN_GROUPS()

@@ -46,7 +46,8 @@ constexpr unsigned long long kTotalMask = (1ull << kTotalShift) - 1;
 constexpr unsigned long long kLookbackTimeoutNs = 2000ull * 1000 * 1000; // a predecessor that never shows up: report, do not hang
 // Work.bad_text bits: 1 = text byte >= 4 on the 2-bit path, 4 = a warp's reservation log overflowed (reported as overflow)
 // ScanArgs.tune bits
-constexpr uint32_t kTuneCoopVerify = 1u;
+constexpr uint32_t kTuneCoopVerify = 1u;       // candidates of a tile may be checked cooperatively (compacted list, lane i checks candidate i)
+constexpr uint32_t kTuneLaneLocalDefault = 3;  // ... when the warp has more than this many (bits 8..15 of tune); fewer: every lane checks its own
 
 constexpr uint32_t kWorkRing = 4, kScratchRing = 3;
 
@@ -79,6 +80,8 @@ struct ScanArgs {
 	uint32_t *tile_count;        // matches per tile -> (in the epilogue) exclusive prefix within the owning CTA
 	unsigned long long *cta_total; // matches per CTA
 	uint32_t stages;             // ring depth of the per-warp tile pipeline
+	uint32_t s_rmask, s_f2, s_cnt; // shared addresses of the offset masks, the stage-2 bitmap and the per-tile counts (api.cu
+	                             // computes the layout of scan_kernel.cuh once per launch; the kernel checks it)
 	uint32_t cnt_cap;            // per-tile counts of the first cnt_cap tiles of a span live in shared memory
 	uint32_t epoch;              // launch number of this matcher: selects the Work copy
 	// multi-GPU count exchange over NVLink peer memory: every rank's mailbox is uint64[kPeerRing][world]
@@ -88,6 +91,7 @@ struct ScanArgs {
 	int append;                  // 1: add to ctl->result instead of replacing it (chunked host text)
 	int pdl;                     // 1: launched as a programmatic dependent launch (consecutive scans may overlap)
 	uint32_t tune;               // kTune* bits
+	uint32_t lane_local;         // tiles with at most this many candidates: every lane checks its own (more: cooperatively, while they fit the list)
 	uint32_t packed_in;          // 1: text16 holds the text already packed 4 symbols per byte (host-side packer of
 	                             // acwm_search_host, alphabet <= 4): data_lo = 0, buffer zero-padded to 16 bytes
 	unsigned long long *trace;   // instrumentation (acwm_set_trace): kTraceWords of %globaltimer stamps per CTA, else NULL
@@ -154,16 +158,61 @@ __device__ __forceinline__ uint64_t encode_stage(uint64_t tile, uint32_t rank, u
 	return (tile << (kRankBits + kPosBits)) | ((uint64_t) rank << kPosBits) | pos;
 }
 
-// ------------------------------------------------------------ mbarrier / TMA bulk copy
+// ------------------------------------------------------------ shared memory by 32-bit shared-space address
+// Everything the scan loop touches in shared memory is addressed by its 32-bit shared-space address (computed once
+// from the dynamic shared-memory base): plain LDS / STS / SYNCS with register + immediate addressing, no generic
+// pointers (whose conversion the compiler rematerialises at every use).  The asm statements are volatile: the slots
+// they read are rewritten by TMA copies and by other lanes between iterations.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+constexpr uint32_t kDynSmemBase = 0x400; // shared address of the dynamic shared memory (scan_kernel checks it)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+	uint4 r;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+	return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+	uint32_t v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
+	unsigned long long v;
+	asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+	return v;
+}
+// One ticket per warp without a divergent region: EVERY lane adds 1 at its own address -- lane 0 at the ticket counter,
+// the others at scratch words of their own -- so the compiler sees a plain full-warp ATOMS (an atomic under
+// `if (lane == 0)` is rewritten into a vote / popc / elect sequence of a dozen instructions).
+__device__ __forceinline__ uint32_t atoms_add1(uint32_t a) {
+	uint32_t old;
+	asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(a) : "memory");
+	return old;
+}
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// ------------------------------------------------------------ mbarrier / TMA bulk copy
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 	asm volatile(
 			"{\n"
 			".reg .pred p;\n"
@@ -172,26 +221,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 			"@p bra DONE_%=;\n"
 			"bra WAIT_%=;\n"
 			"DONE_%=:\n"
-			"}\n" ::"r"(smem_u32(bar)),
+			"}\n" ::"r"(bar),
 			"r"(parity)
 			: "memory");
 }
-// L2 policy for the text stream: read once, evict first (keeps L2-resident tables in place)
-__device__ __forceinline__ uint64_t policy_evict_first() {
-	uint64_t pol;
-	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-	return pol;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-	uint64_t pol;
-	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-	return pol;
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+// L2 policies of createpolicy.fractional.L2::evict_first / evict_last (fraction 1.0), as the constants they encode to:
+// the text stream is read once and evicted first (keeps L2-resident tables in place), tables are kept
+constexpr unsigned long long kPolicyEvictFirst = 0x12F0000000000000ull, kPolicyEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, unsigned long long pol) {
 	asm volatile(
-			"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-					smem_u32(dst)),
-			"l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+			"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+			"l"(src), "r"(bytes), "r"(bar), "l"(pol)
 			: "memory");
 }
 
@@ -248,64 +288,65 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 // Warp-level staging of the matches of one tile.  A warp reserves staging slots from the launch's cursor in
 // blocks that double in size (one global atomic per block, not per tile) and logs its blocks in shared
-// memory: when the scan is over the warp itself moves its matches to their sorted places.
+// memory: when the scan is over the warp itself moves its matches to their sorted places.  The entries of one
+// tile are contiguous: a tile that does not fit what is left of the current block leaves that tail unused (the
+// block's log entry shrinks) and starts a new block.
 struct Emitter {
 	const ScanArgs *a;
 	Work *wk;
-	uint32_t *s_cnt;             // shared-memory per-tile counts (first a->cnt_cap tiles of the span)
-	unsigned long long *log;     // this warp's reservations: [slots : 24 | first slot : 40]
+	uint32_t s_cnt;              // shared address of the per-tile counts (first a->cnt_cap tiles of the span; zeroed in the prologue)
+	uint32_t log_s;              // shared address of this warp's reservations: [slots : 24 | first slot : 40]
 	uint64_t tile;
 	uint32_t idx;                // span-relative index of the tile
 	unsigned long long warp_count;
-	unsigned long long blk_ptr, old_ptr, new_ptr;
-	uint32_t blk_left, old_left;
+	unsigned long long blk_ptr;  // next free slot of the current block
+	uint32_t blk_left;
 	uint32_t n_log, lost;        // reservations logged / more reservations than the log holds (reported as overflow)
+	uint64_t *tile_slots;        // where entry 0 of the current tile goes (nullptr: the staging array is full)
+	uint64_t tile_word;          // the current tile's number in place: tile << (kRankBits + kPosBits)
 
 	// warp-uniform: make room for `total` entries of the current tile
 	__device__ __forceinline__ void reserve(uint32_t total) {
-		old_ptr = blk_ptr;
-		old_left = blk_left;
-		new_ptr = 0;
 		if (total > blk_left) {
-			const uint32_t extra = total - blk_left;
-			const uint32_t grab = max(extra, kStageBlock << min(n_log, kMaxGrabLog2 - kStageBlockLog2));
+			const uint32_t grab = max(total, kStageBlock << min(n_log, kMaxGrabLog2 - kStageBlockLog2));
 			unsigned long long p = 0;
 			if (lane_id() == 0) {
+				if (n_log && !lost) // the unused tail of the block we leave
+					sts64(log_s + 8u * (n_log - 1), lds64(log_s + 8u * (n_log - 1)) - ((unsigned long long) blk_left << 40));
 				p = atomicAdd(&wk->cursor, (unsigned long long) grab);
 				if (n_log < kLogCap)
-					log[n_log] = ((unsigned long long) grab << 40) | p;
+					sts64(log_s + 8u * n_log, ((unsigned long long) grab << 40) | p);
 			}
 			if (n_log < kLogCap)
 				n_log++;
 			else
 				lost = 1;
-			new_ptr = __shfl_sync(kFull, p, 0);
-			blk_ptr = new_ptr + extra;
-			blk_left = grab - extra;
-		} else {
-			blk_ptr += total;
-			blk_left -= total;
+			blk_ptr = __shfl_sync(kFull, p, 0);
+			blk_left = grab;
 		}
+		tile_slots = blk_ptr + total <= a->stage_cap ? a->staging + blk_ptr : nullptr;
+		tile_word = tile << (kRankBits + kPosBits);
+		blk_ptr += total;
+		blk_left -= total;
 	}
 	// entry k (= rank in the tile) of the current reservation
 	__device__ __forceinline__ void put(uint32_t k, uint32_t pos) const {
-		const unsigned long long slot = k < old_left ? old_ptr + k : new_ptr + (k - old_left);
-		if (slot < a->stage_cap)
-			a->staging[slot] = encode_stage(tile, k, pos);
+		if (tile_slots)
+			tile_slots[k] = tile_word + (((uint64_t) k << kPosBits) | pos);
 	}
 	__device__ __forceinline__ void end_tile(uint32_t total) {
 		if (a->want_positions && lane_id() == 0) {
-			if (idx < a->cnt_cap)
-				s_cnt[idx] = total;
-			else
+			if (idx >= a->cnt_cap)
 				a->tile_count[tile] = total;
+			else if (total)
+				sts32(s_cnt + 4u * idx, total);
 		}
 		warp_count += total;
 	}
-	// blocks fill up in order: only the last one has an unused tail
+	// the last block keeps an unused tail as well
 	__device__ __forceinline__ void finish() const {
 		if (lane_id() == 0 && n_log && !lost)
-			log[n_log - 1] -= (unsigned long long) blk_left << 40;
+			sts64(log_s + 8u * (n_log - 1), lds64(log_s + 8u * (n_log - 1)) - ((unsigned long long) blk_left << 40));
 	}
 };
 
@@ -332,8 +373,6 @@ static __device__ __noinline__ uint32_t verify_dfa(const ScanArgs &a, uint64_t e
 
 __device__ __forceinline__ uint32_t verify_window(const ScanArgs &a, uint32_t key, uint64_t e) {
 	const acwm_scan_params &p = a.prm;
-	if (p.verify_kind)
-		return verify_dfa(a, e);
 	const uint32_t b = (uint32_t) (key * p.hb_mult) >> p.hb_sh;
 	const uint32_t lo = __ldg(a.bucket_start + b), hi = __ldg(a.bucket_start + b + 1);
 	uint32_t mult = 0;
@@ -341,6 +380,10 @@ __device__ __forceinline__ uint32_t verify_window(const ScanArgs &a, uint32_t ke
 		const acwm_ventry en = a.entries[i];
 		if (en.key != key)
 			continue;
+		// filtered AC: the automaton decides -- but only windows whose last symbols are those of some pattern get
+		// that far (its walk is m dependent lookups; false positives of the stage-2 bitmap end here, two loads in)
+		if (p.verify_kind)
+			return verify_dfa(a, e);
 		const uint32_t len = en.len & 0x7fffffffu;
 		if (e + 1 < a.data_lo + len || e >= a.data_hi || e < a.report_lo)
 			continue; // window would start before the text / end after it / not ours to report

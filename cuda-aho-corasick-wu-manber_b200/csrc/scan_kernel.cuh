@@ -85,33 +85,39 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	constexpr uint32_t W = THREADS / 32;
 	constexpr bool kPacked = Front::kPacked;
 	constexpr bool kPk = kPacked && !EXACT; // the 2-bit copy of the tile exists for the verification windows only
-	// [CTA scratch 1 KiB][front table][offset masks][stage-2 bitmap][per-warp areas]
-	uint64_t *tab_bar = reinterpret_cast<uint64_t *>(smem);
-	uint32_t *s_next = reinterpret_cast<uint32_t *>(smem + 16); // next unclaimed tile of this CTA's span
+	// [CTA scratch 1 KiB][per-warp areas][front table][offset masks][stage-2 bitmap][per-tile counts]
+	// The scan loop addresses all of it by 32-bit shared-space addresses (see scan_common.cuh).
+	// The dynamic shared memory of a kernel without static shared memory starts at shared address kDynSmemBase (the
+	// first KiB of the window belongs to the system): a CONSTANT, and so are the per-warp areas (base + warp * size)
+	// and the front table behind them: these addresses fold into the immediate field of their LDS / STS / SYNCS.
+	// The tables behind the front table start where the host says (ScanArgs.s_rmask .. s_cnt: one constant-bank
+	// read each).  Both checked here, loudly.
+	constexpr uint32_t sb = kDynSmemBase;
+	constexpr uint32_t stages = kPacked ? 1u : 2u;
+	// ring depth of the per-warp tile pipeline: the 2-bit path copies a tile into registers and re-arms its ONE slot
+	// while it walks; the bytes path walks the raw tile in place and loads the next one into its second slot
+	constexpr uint32_t s_warps = sb + kSmemReserve;
+	constexpr uint32_t s_front = s_warps + W * warp_smem_bytes(stages, kPk);
+	const uint32_t tab_bar = sb;
+	const uint32_t s_next = sb + 16; // next unclaimed tile of this CTA's span
 	uint32_t *s_bad = reinterpret_cast<uint32_t *>(smem + 20);
 	unsigned long long *s_count = reinterpret_cast<unsigned long long *>(smem + 24); // matches of this CTA
 	unsigned long long *s_misc = reinterpret_cast<unsigned long long *>(smem + 32);  // [0] cursor, [1] append base
-	uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + 64); // 33 words
 	const uint32_t front_smem = a.front_in_smem ? ((a.front_bytes + 15u) & ~15u) : 0u;
 	// tables too large for shared memory stay in global memory (L2-resident: access-policy window + evict_first text)
 	const uint32_t rm_bytes = (EXACT || !a.prm.r_in_smem) ? 0u : ((a.prm.r_entries * a.prm.r_entry_bytes + 15u) & ~15u);
 	const uint32_t f2_bytes = (EXACT || !a.prm.f2_in_smem) ? 0u : ((a.prm.f2_words * 4u + 15u) & ~15u);
-	uint8_t *s_front = smem + kSmemReserve;
-	uint8_t *s_rmask = s_front + front_smem;
-	uint32_t *s_f2 = reinterpret_cast<uint32_t *>(s_rmask + rm_bytes);
-	uint8_t *s_warps = s_rmask + rm_bytes + f2_bytes;
+	const uint32_t s_rmask = a.s_rmask, s_f2 = a.s_f2, s_cnt = a.s_cnt;
+	if (smem_u32(smem) != sb || s_rmask != s_front + front_smem || s_f2 != s_rmask + rm_bytes || s_cnt != s_f2 + f2_bytes)
+		__trap();
 
 	const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-	// ring depth of the per-warp tile pipeline: the 2-bit path copies a tile into registers and re-arms its ONE slot
-	// while it walks; the bytes path walks the raw tile in place and loads the next one into its second slot
-	constexpr uint32_t stages = kPacked ? 1u : 2u;
-	uint8_t *wbase = s_warps + warp * warp_smem_bytes(stages, kPk);
-	uint8_t *bufs = wbase;
-	uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + stages * kBufBytes);
-	uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + stages * kBufBytes + (kPk ? kPackWords * 4 : 0));
-	uint16_t *lst = reinterpret_cast<uint16_t *>(bars + 2 * kMaxStages);  // match positions of the current tile
-	unsigned long long *wlog = reinterpret_cast<unsigned long long *>(lst + kListCap); // this warp's staging reservations
-	uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_warps + W * warp_smem_bytes(stages, kPk)); // a.cnt_cap words
+	const uint32_t wbase = s_warps + warp * warp_smem_bytes(stages, kPk);
+	const uint32_t pk = wbase + stages * kBufBytes;
+	const uint32_t bars = pk + (kPk ? kPackWords * 4 : 0);
+	const uint32_t lst = bars + 16 * kMaxStages;      // match positions of the current tile (uint16)
+	const uint32_t wlog = lst + 2 * kListCap;         // this warp's staging reservations (uint64)
+	uint32_t *s_cnt_p = reinterpret_cast<uint32_t *>(smem + (s_cnt - sb)); // a.cnt_cap words
 
 	// this CTA's span of warp tiles; the warps claim its tiles one at a time (shared-memory ticket)
 	const uint64_t cta_lo = min(a.tile_lo + (uint64_t) blockIdx.x * a.tiles_per_cta, a.tile_hi);
@@ -129,27 +135,25 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 			a.trace[(size_t) blockIdx.x * kTraceWords + 11] = smid;
 		}
 		mbar_init(tab_bar, 1);
-		*s_next = stages * W;
+		sts32(s_next, stages * W);
 		*s_bad = 0;
 		*s_count = 0;
 	}
 	if (lane == 0)
 		for (uint32_t s = 0; s < stages; s++)
-			mbar_init(&bars[s], 1);
+			mbar_init(bars + 8 * s, 1);
 	if (lane < 4)
 		for (uint32_t s = 0; s < stages; s++) // pad behind each buffer: read, never used
-			reinterpret_cast<uint32_t *>(bufs + s * kBufBytes + kLoadBytes)[lane] = 0;
+			sts32(wbase + s * kBufBytes + kLoadBytes + 4 * lane, 0);
 	if (kPk && lane < 3)
-		pk[kPackWords - 3 + lane] = 0;
+		sts32(pk + 4 * (kPackWords - 3 + lane), 0);
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncwarp();
 
-	// Per-warp pipeline state, all in registers: slot s holds (or is receiving) tile slot_idx[s] of the span; a tile
-	// that lies inside the text arrives by ONE TMA bulk copy (slot_tma[s], its mbarrier's phase in slot_phase[s]),
-	// the first / last tiles of the text through the careful loader.
-	uint32_t slot_idx[stages], slot_tma[stages], slot_phase[stages];
-	uint8_t *slot_buf[stages];
-	uint64_t *slot_bar[stages];
+	// Per-warp pipeline state, all in registers: slot s holds (or is receiving) tile slot_idx[s] of the span.  Every
+	// tile completes one phase of its slot's mbarrier: a tile that lies inside the text arrives by ONE TMA bulk copy
+	// (complete_tx), the first / last tiles of the text go through the careful loader, which then arrives itself.
+	uint32_t slot_idx[stages] = {}, slot_phase[stages] = {}, slot_buf[stages] = {}, slot_bar[stages] = {};
 	// what a tile's copy needs, computed once: tiles [1, int_hi) lie inside the text, tile t is loaded from
 	// tile0 + t * tile_stride (load_bytes bytes: history + tile)
 	const bool packed_in = kPacked && a.packed_in;
@@ -166,52 +170,49 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 		if (idx >= n_b)
 			return;
 		const uint32_t t = cta_lo32 + idx;
-		uint8_t *dst = slot_buf[s];
-		if (t >= 1u && t < int_hi) {
+		if (t - 1u < int_hi - 1u) { // 1 <= t < int_hi (int_hi = 0: never)
 			if (lane == 0) {
-				const uint64_t stream_pol = policy_evict_first(); // made where it is used: not two registers held across the scan
 				mbar_expect_tx(slot_bar[s], load_bytes);
-				tma_bulk_g2s(dst, tile0 + (uint64_t) t * tile_stride, load_bytes, slot_bar[s], stream_pol);
+				tma_bulk_g2s(slot_buf[s], tile0 + (uint64_t) t * tile_stride, load_bytes, slot_bar[s], kPolicyEvictFirst);
 			}
-			slot_tma[s] = 1;
 		} else {
+			uint8_t *dst = smem + (slot_buf[s] - sb);
 			if (packed_in)
 				load_tile_edge_packed(a, t, dst);
 			else
 				load_tile_edge(a, t, dst);
-			slot_tma[s] = 0;
+			__syncwarp(); // every lane's part of the tile is written before lane 0 releases it
+			if (lane == 0)
+				mbar_arrive(slot_bar[s]);
 		}
 	};
 	// claim the next tile of the span for ring slot s and start loading it
-	auto refill = [&](uint32_t s) {
-		uint32_t idx = 0;
-		if (lane == 0)
-			idx = atomicAdd(s_next, 1u);
-		issue(s, __shfl_sync(kFull, idx, 0));
-	};
+	// (lane 0 draws the ticket; the other lanes' adds go to words of the warp's match list, which holds nothing
+	// between two tiles)
+	const uint32_t tick = lane == 0 ? s_next : lst + 4 * lane;
+	auto refill = [&](uint32_t s) { issue(s, __shfl_sync(kFull, atoms_add1(tick), 0)); };
 #pragma unroll
 	for (uint32_t s = 0; s < stages; s++) {
 		slot_phase[s] = 0;
-		slot_buf[s] = bufs + s * kBufBytes;
-		slot_bar[s] = &bars[s];
+		slot_buf[s] = wbase + s * kBufBytes;
+		slot_bar[s] = bars + 8 * s;
 		issue(s, s * W + warp);
 	}
 
 	// tables: global -> shared with TMA bulk copies, overlapped with the first text tiles
 	if (threadIdx.x == 0) {
 		if (tab_bytes) {
-			const uint64_t keep = policy_evict_last();
 			mbar_expect_tx(tab_bar, tab_bytes);
 #pragma unroll 1
 			for (uint32_t off = 0; off < front_smem; off += 16384)
-				tma_bulk_g2s(s_front + off, a.front + off, min(16384u, front_smem - off), tab_bar, keep);
+				tma_bulk_g2s(s_front + off, a.front + off, min(16384u, front_smem - off), tab_bar, kPolicyEvictLast);
 #pragma unroll 1
 			for (uint32_t off = 0; off < rm_bytes; off += 16384)
-				tma_bulk_g2s(s_rmask + off, a.rmask + off, min(16384u, rm_bytes - off), tab_bar, keep);
+				tma_bulk_g2s(s_rmask + off, a.rmask + off, min(16384u, rm_bytes - off), tab_bar, kPolicyEvictLast);
 #pragma unroll 1
 			for (uint32_t off = 0; off < f2_bytes; off += 16384)
-				tma_bulk_g2s(reinterpret_cast<uint8_t *>(s_f2) + off, reinterpret_cast<const uint8_t *>(a.filter2) + off,
-						min(16384u, f2_bytes - off), tab_bar, keep);
+				tma_bulk_g2s(s_f2 + off, reinterpret_cast<const uint8_t *>(a.filter2) + off, min(16384u, f2_bytes - off), tab_bar,
+						kPolicyEvictLast);
 		}
 		trace_mark(a, 1);
 	}
@@ -224,6 +225,10 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 		__stcg(&nxt->bad_text, 0u);
 		__threadfence();
 	}
+	// per-tile counts: a tile without a match never writes its word
+	if (a.want_positions)
+		for (uint32_t i = threadIdx.x; i < min(n_b, a.cnt_cap); i += THREADS)
+			s_cnt_p[i] = 0;
 	__syncthreads(); // the ticket, the table barrier and the CTA counters are set up
 	if (a.pdl)
 		pdl_trigger(); // overlap mode: the next scan of the stream may take over SMs as our CTAs retire
@@ -242,13 +247,18 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	em.idx = 0;
 	em.tile = 0;
 	em.warp_count = 0;
-	em.blk_ptr = em.old_ptr = em.new_ptr = 0;
-	em.blk_left = em.old_left = 0;
-	em.log = wlog;
+	em.blk_ptr = 0;
+	em.blk_left = 0;
+	em.log_s = wlog;
 	em.n_log = em.lost = 0;
+	em.tile_slots = nullptr;
+	em.tile_word = 0;
 	Front fr;
-	const TabRef f2{smem_u32(s_f2), reinterpret_cast<const uint8_t *>(a.filter2), a.prm.f2_in_smem != 0};
-	fr.init(s_front, TabRef{smem_u32(s_rmask), a.rmask, a.prm.r_in_smem != 0}, a);
+	const TabRef f2{s_f2, reinterpret_cast<const uint8_t *>(a.filter2), a.prm.f2_in_smem != 0};
+	fr.init(s_front, TabRef{s_rmask, a.rmask, a.prm.r_in_smem != 0}, a);
+	// candidates of a tile are checked by the lanes that found them while they are few (<= lane_local), by the
+	// whole warp from a compacted list while they fit it (<= kListCap), and lane by lane again beyond that
+	const uint32_t lane_local = a.lane_local;
 
 	bool tab_ready = tab_bytes == 0; // the tables are first needed by walk(): the first tile is loaded and packed under their copy
 	for (;;) {
@@ -257,13 +267,10 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 		if (idx >= n_b)
 			break; // the span is exhausted (claims are handed out in ascending order)
 		const uint64_t tile = cta_lo + idx;
-		if (slot_tma[0]) {
-			mbar_wait(slot_bar[0], slot_phase[0]);
-			slot_phase[0] ^= 1u;
-		}
-		__syncwarp();
+		mbar_wait(slot_bar[0], slot_phase[0]); // every lane sees the phase flip itself: the tile is visible to it
+		slot_phase[0] ^= 1u;
 
-		const uint8_t *buf = slot_buf[0];
+		const uint32_t buf = slot_buf[0];
 		fr.load(a, buf, pk, badacc);
 		if constexpr (kPacked) { // the tile now lives in registers (+ pk): refill the slot while we walk
 			__syncwarp();
@@ -320,10 +327,11 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 #pragma unroll
 						for (int g = 0; g < Front::kWords; g++)
 							for (uint32_t w = fr.hw[g]; w; w &= w - 1)
-								lst[k++] = (uint16_t) (lane * kLane + Front::sym_of(g, __ffs(w) - 1));
+								sts16(lst + 2 * k++, lane * kLane + Front::sym_of(g, __ffs(w) - 1));
 						__syncwarp();
 						for (uint32_t i = lane; i < total; i += 32)
-							em.put(i, lst[i]);
+							em.put(i, lds_u16(lst + 2 * i));
+						__syncwarp(); // the list is free again
 					} else {
 #pragma unroll
 						for (int g = 0; g < Front::kWords; g++)
@@ -333,8 +341,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 				}
 			}
 		} else {
-			if constexpr (kPacked)
-				__syncwarp(); // the 2-bit copy of the tile (pk) is complete
+			// (2-bit path: the copy of the tile in pk is complete, the warp met after load())
 			// candidates -> offset mask -> stage-2 bitmap -> buckets; survivors become bits of mw (chunk-relative
 			// end positions) of the lane that owns the chunk
 			uint32_t mw0 = 0, mw1 = 0, mw2 = 0, mw3 = 0, multi = 0;
@@ -361,20 +368,20 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 			const uint32_t tot_c = __reduce_add_sync(kFull, ncand);
 			if (tot_c == 0) {
 				// the usual tile of a selective filter
-			} else if ((a.tune & kTuneCoopVerify) && tot_c <= kListCap) {
-				// few candidates, unevenly spread over the lanes: compact them into the warp's list and let
+			} else if (tot_c > lane_local && tot_c <= kListCap) {
+				// candidates unevenly spread over the lanes: compact them into the warp's list and let
 				// lane i check candidate i (one pass instead of max-per-lane divergent iterations)
 				uint32_t k = warp_incl_scan(ncand) - ncand;
 #pragma unroll
 				for (int g = 0; g < Front::kWords; g++)
 					for (uint32_t w = fr.hw[g]; w; w &= w - 1)
-						lst[k++] = (uint16_t) (lane * kLane + Front::sym_of(g, __ffs(w) - 1));
+						sts16(lst + 2 * k++, lane * kLane + Front::sym_of(g, __ffs(w) - 1));
 				__syncwarp();
 				for (uint32_t base = 0; base < tot_c; base += 32) {
 					const uint32_t i = base + lane;
 					uint32_t cpos = 0, sv = 0, mu = 0;
 					if (i < tot_c) {
-						cpos = lst[i];
+						cpos = lds_u16(lst + 2 * i);
 						uint32_t rm = fr.probe_mask(a, buf, pk, cpos);
 						while (rm) {
 							const uint32_t r = (uint32_t) (__ffs(rm) - 1);
@@ -392,20 +399,20 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 						const int src = __ffs(any) - 1;
 						any &= any - 1;
 						const uint32_t cp = __shfl_sync(kFull, cpos, src);
-						uint32_t sb = __shfl_sync(kFull, sv, src);
+						uint32_t sbits = __shfl_sync(kFull, sv, src);
 						const uint32_t m2 = __shfl_sync(kFull, mu, src);
 						const uint32_t owner = cp / kLane;
 						if (lane == owner) {
 							const uint32_t c = cp - owner * kLane;
-							for (; sb; sb &= sb - 1)
-								set_mw(c + (uint32_t) (__ffs(sb) - 1));
+							for (; sbits; sbits &= sbits - 1)
+								set_mw(c + (uint32_t) (__ffs(sbits) - 1));
 							multi |= m2;
 						}
 					}
 				}
 				__syncwarp(); // the list is reused for the match positions below
 			} else {
-				// many candidates: every lane checks its own
+				// few candidates (a couple per lane at most) or very many: every lane checks its own
 #pragma unroll
 				for (int g = 0; g < Front::kWords; g++) {
 					uint32_t w = fr.hw[g];
@@ -433,15 +440,18 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 				return verify_window(a, key, tile_start + lane * kLane + p);
 			};
 			const uint32_t mw[4] = {mw0, mw1, mw2, mw3};
-			uint32_t cnt = __popc(mw0) + __popc(mw1) + __popc(mw2) + __popc(mw3);
-			if (multi) {
-				cnt = 0;
+			uint32_t cnt = 0;
+			if (tot_c) {
+				cnt = __popc(mw0) + __popc(mw1) + __popc(mw2) + __popc(mw3);
+				if (multi) {
+					cnt = 0;
 #pragma unroll
-				for (int g = 0; g < 4; g++)
-					for (uint32_t w = mw[g]; w; w &= w - 1)
-						cnt += mult_at(32 * g + __ffs(w) - 1);
+					for (int g = 0; g < 4; g++)
+						for (uint32_t w = mw[g]; w; w &= w - 1)
+							cnt += mult_at(32 * g + __ffs(w) - 1);
+				}
 			}
-			if (__any_sync(kFull, cnt != 0)) {
+			if (tot_c && __any_sync(kFull, cnt != 0)) {
 				const uint32_t incl = warp_incl_scan(cnt);
 				total = __shfl_sync(kFull, incl, 31);
 				if (a.want_positions) {
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 							const uint32_t reps = multi ? mult_at(p) : 1u;
 							for (uint32_t i = 0; i < reps; i++, k++) {
 								if (listed)
-									lst[k] = (uint16_t) (lane * kLane + p);
+									sts16(lst + 2 * k, lane * kLane + p);
 								else
 									em.put(k, lane * kLane + p);
 							}
@@ -463,21 +473,21 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 					if (listed) {
 						__syncwarp();
 						for (uint32_t i = lane; i < total; i += 32)
-							em.put(i, lst[i]);
+							em.put(i, lds_u16(lst + 2 * i));
 					}
 				}
 			}
+			__syncwarp(); // every lane is done with this slot (bytes path), pk and the list before they are rewritten
 		}
 		em.end_tile(total);
-		__syncwarp(); // every lane is done with this slot (and pk) before it is refilled / rewritten
 		if constexpr (!kPacked) { // refill the slot just walked, then the other slot (loaded meanwhile) becomes slot 0
+			if constexpr (EXACT)
+				__syncwarp();
 			refill(0);
-			const uint32_t ti = slot_idx[0], tt = slot_tma[0], tp = slot_phase[0];
-			uint8_t *tb = slot_buf[0];
-			uint64_t *tr = slot_bar[0];
-			slot_idx[0] = slot_idx[stages - 1], slot_tma[0] = slot_tma[stages - 1], slot_phase[0] = slot_phase[stages - 1];
+			const uint32_t ti = slot_idx[0], tp = slot_phase[0], tb = slot_buf[0], tr = slot_bar[0];
+			slot_idx[0] = slot_idx[stages - 1], slot_phase[0] = slot_phase[stages - 1];
 			slot_buf[0] = slot_buf[stages - 1], slot_bar[0] = slot_bar[stages - 1];
-			slot_idx[stages - 1] = ti, slot_tma[stages - 1] = tt, slot_phase[stages - 1] = tp;
+			slot_idx[stages - 1] = ti, slot_phase[stages - 1] = tp;
 			slot_buf[stages - 1] = tb, slot_bar[stages - 1] = tr;
 		}
 	}
@@ -515,7 +525,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 					const uint32_t i = base + lane * 8 + k;
 					v[k] = 0;
 					if (i < n_b)
-						v[k] = i < a.cnt_cap ? s_cnt[i] : __ldcg(a.tile_count + cta_lo + i);
+						v[k] = i < a.cnt_cap ? s_cnt_p[i] : __ldcg(a.tile_count + cta_lo + i);
 					sum += v[k];
 				}
 				const uint32_t incl = warp_incl_scan(sum);
@@ -525,7 +535,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 					const uint32_t i = base + lane * 8 + k;
 					if (i < n_b) {
 						if (i < a.cnt_cap)
-							s_cnt[i] = run;
+							s_cnt_p[i] = run;
 						else
 							a.tile_count[cta_lo + i] = run;
 					}
@@ -649,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 		// every warp moves what it staged: entry -> positions[span base + tile offset + rank]
 		constexpr int kBatch = 4;
 		for (uint32_t d = 0; d < em.n_log; d++) {
-			const unsigned long long desc = em.log[d];
+			const unsigned long long desc = lds64(em.log_s + 8u * d);
 			const unsigned long long ptr = desc & ((1ull << 40) - 1);
 			const uint32_t len = (uint32_t) (desc >> 40);
 			for (uint32_t i0 = lane; i0 < len; i0 += 32 * kBatch) {
@@ -667,7 +677,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 					const uint32_t rank = (uint32_t) (e[u] >> kPosBits) & ((1u << kRankBits) - 1);
 					const uint32_t pos = (uint32_t) e[u] & ((1u << kPosBits) - 1);
 					const uint64_t ti = tile - cta_lo;
-					const uint32_t off = ti < a.cnt_cap ? s_cnt[ti] : __ldcg(a.tile_count + tile);
+					const uint32_t off = ti < a.cnt_cap ? s_cnt_p[ti] : __ldcg(a.tile_count + tile);
 					const unsigned long long at = span_base + off + rank;
 					if (at < a.cap)
 						a.positions[at] = tile * kTile + pos - a.data_lo;

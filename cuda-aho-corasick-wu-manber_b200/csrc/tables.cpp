@@ -404,7 +404,7 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 	prm.exact_front = (bestD == m) ? 1 : 0;
 	prm.n_rows = n_rows;
 	// two chains per lane (scan_packed.cu): the second chain repeats ceil((depth - 1) / K) warm-up lookups
-	prm.ilp = (K == 3 && !global && prm.exact_front && bestD <= 16 && getenv("ACWM_NO_ILP") == nullptr) ? 2 : 1;
+	prm.ilp = (K == 3 && !global && prm.exact_front && bestD <= 13 && getenv("ACWM_NO_ILP") == nullptr) ? 2 : 1;
 	if (!prm.exact_front)
 		build_verify(ps, true, opts, c, prof);
 	c.info.table_in_smem = global ? 0 : 1;
