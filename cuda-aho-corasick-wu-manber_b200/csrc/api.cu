@@ -295,22 +295,26 @@ __global__ void collect_last_kernel(Control *ctl, const unsigned long long *box,
 // The packer threads run ahead through the text; this thread takes the chunks in order (and packs along while it
 // waits), sends each one and launches its scan.
 constexpr uint64_t kHostPackMin = 4ull << 20;
-constexpr unsigned kHostPackMinThreads = 10;
+constexpr unsigned kHostPackMinThreads = 3; // fewer: the text goes one byte per symbol (the ranks of a torchrun box share its cores)
 constexpr uint64_t kPackChunk = 56 * HostPacker::kPieceSymbols; // 14 Mi symbols = 4096 tiles = 56 work items
 constexpr unsigned kPackRing = 16;
 static_assert(kPackChunk % kTile == 0 && kPackChunk % 64 == 0, "chunks are whole tiles and whole 16-byte pieces");
-// Share (percent) of a pinned host text that is sent unpacked beside the packed rest.  ACWM_HOST_RAW_PERCENT sets it
-// (0 = none); by default it follows the packer's thread count: link time n(r + (1-r)/4)/L and packing time n(1-r)/P
-// meet at r = (1/P - 1/4L) / (3/4L + 1/P), with P = 5.2 GB/s per packer thread on text that comes from DRAM and
-// L = 56 GB/s for the link (fit on the 16-core box, profiles/README.md session q: 15 threads -> 32 %, where 30 % beat
-// 22 % by 10 %; a text that is still in the host's caches packs faster and would take less).  Kept within 10..35 %.
-static unsigned host_raw_percent(unsigned threads) {
-	const char *e = getenv("ACWM_HOST_RAW_PERCENT");
-	if (e && *e)
-		return (unsigned) std::min<long>(std::max<long>(atol(e), 0), 90);
+// Share of a pinned host text that is sent unpacked beside the packed rest.  ACWM_HOST_RAW_PERCENT fixes it
+// (0 = none).  Otherwise the FIRST search of a matcher takes it from the packer's thread count: link time
+// n(r + (1-r)/4)/L and packing time n(1-r)/P meet at r = (1/P - 1/4L) / (3/4L + 1/P), with P = 5.2 GB/s per packer
+// thread on text that comes from DRAM and L = 56 GB/s for the link (fit on a 16-core box, profiles/README.md session
+// q) -- and every search then MEASURES both sides (events around the raw copies and around the packed copies) and
+// moves the share towards the point where they take equally long.  What the link and the cores really deliver
+// depends on who else uses them (eight ranks of one box share its cores, its memory and its PCIe root), so the
+// share follows the box instead of a model of it.
+static double host_raw_share_model(unsigned threads) {
 	const double P = 5.2 * std::max(1u, threads), L = 56.0;
 	const double r = (1.0 / P - 0.25 / L) / (0.75 / L + 1.0 / P);
-	return (unsigned) std::min(35.0, std::max(10.0, 100.0 * r + 0.5));
+	return std::min(0.6, std::max(0.1, r));
+}
+static int host_raw_percent_env() {
+	const char *e = getenv("ACWM_HOST_RAW_PERCENT");
+	return e && *e ? (int) std::min<long>(std::max<long>(atol(e), 0), 90) : -1;
 }
 // ACWM_HOST_PACK: 0 = never, 2 = always (tests), unset / 1 = when the host has the cores for it
 static int host_pack_mode() {
@@ -362,17 +366,18 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		HostPacker &p;
 		~Release() { p.finish(); }
 	} release{pk};
-	// The link moves raw text by DMA while the cores pack: a prefix of the text (whole chunks, host_raw_percent: about
+	// The link moves raw text by DMA while the cores pack: a prefix of the text (whole chunks; the share: see host_raw_share_model above, about
 	// where link time and packing time meet) goes one byte per symbol from the caller's
 	// PINNED buffer on a second copy stream, the rest is packed.  The packed part brings its own history (the 64-symbol
 	// halo of its first tile and the reach of the longest pattern's compare), packed by this thread.
 	uint64_t R = 0;
 	const uint32_t H = (std::max<uint32_t>(64u, mt->c.prm.m_max) + 63u) & ~63u;
-	const unsigned raw_pct = host_raw_percent(mt->packer->threads());
-	if (n_chunks >= 5 && H <= 4096 && raw_pct > 0) {
+	const int raw_env = host_raw_percent_env();
+	const double raw_share = raw_env >= 0 ? raw_env / 100.0 : (mt->raw_share >= 0 ? mt->raw_share : host_raw_share_model(mt->packer->threads()));
+	if (n_chunks >= 5 && H <= 4096 && raw_share > 0) {
 		cudaPointerAttributes at;
 		if (cudaPointerGetAttributes(&at, text) == cudaSuccess && at.type == cudaMemoryTypeHost)
-			R = std::min<uint64_t>(n_chunks - 1, (n_chunks * raw_pct + 50) / 100);
+			R = std::min<uint64_t>(n_chunks - 1, (uint64_t) (n_chunks * raw_share + 0.5));
 		(void) cudaGetLastError();
 	}
 	const uint64_t n_raw = R * kPackChunk;
@@ -388,7 +393,10 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		if (!mt->s_copy2) {
 			CU(cudaStreamCreateWithFlags(&mt->s_copy2, cudaStreamNonBlocking));
 			CU(cudaMallocHost((void **) &mt->h_hist, 4096 / 4 + 16));
+			for (auto &e : mt->ev_hyb)
+				CU(cudaEventCreate(&e));
 		}
+		CU(cudaEventRecord(mt->ev_hyb[0], mt->s_copy2));
 	}
 	pk.begin(text + n_raw, n - n_raw, kPackChunk, mt->h_pack_ring, slot_bytes, kPackRing);
 	for (uint64_t ci = 0; ci < R; ci++) { // the raw prefix: all copies and scans queued at once
@@ -404,6 +412,8 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		CU(cudaEventRecord(mt->ev_time[2 * ci + 1], mt->s_scan));
 	}
 	if (R) {
+		CU(cudaEventRecord(mt->ev_hyb[1], mt->s_copy2));
+		CU(cudaEventRecord(mt->ev_hyb[2], mt->s_copy));
 		HostPacker::pack_now(text + n_raw - H, mt->h_hist, H);
 		CU(cudaMemcpyAsync(mt->d_text + (n_raw - H) / 4, mt->h_hist, H / 4, cudaMemcpyHostToDevice, mt->s_copy));
 	}
@@ -438,12 +448,30 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 			pk.recycle(oldest++); // let the packers run further ahead
 	}
 	(void) cudaGetLastError(); // cudaEventQuery's cudaErrorNotReady is not an error
+	if (R)
+		CU(cudaEventRecord(mt->ev_hyb[3], mt->s_copy));
 	const uint64_t bad = pk.bad();
 	mt->last_h2d_bytes = n_raw + (packed_total - n_raw / 4) + (R ? H / 4 : 0);
 	mt->last_want_positions = want_positions;
 	const double t_issue = now();
 	rc = acwm_fetch(mt, count, positions, cap, n_written, mt->s_scan);
 	pk.finish();
+	if (R && raw_env < 0 && cudaStreamSynchronize(mt->s_copy) == cudaSuccess && cudaStreamSynchronize(mt->s_copy2) == cudaSuccess) {
+		// both sides started together: per chunk, the raw side took t_raw / R and the packed side t_pk / (n_chunks - R);
+		// they finish together at R* = n_chunks * b / (a + b) (a, b = time per raw / per packed chunk).  Half-way there.
+		float t_raw = 0, t_pk = 0;
+		if (cudaEventElapsedTime(&t_raw, mt->ev_hyb[0], mt->ev_hyb[1]) == cudaSuccess
+				&& cudaEventElapsedTime(&t_pk, mt->ev_hyb[2], mt->ev_hyb[3]) == cudaSuccess && t_raw > 0 && t_pk > 0) {
+			const double a = t_raw / (double) R, b = t_pk / (double) (n_chunks - R);
+			const double target = b / (a + b);
+			const double cur = (double) R / (double) n_chunks;
+			mt->raw_share = std::min(0.9, std::max(1.0 / (double) n_chunks, 0.5 * cur + 0.5 * target));
+			if (dbg)
+				fprintf(stderr, "  hybrid: %llu raw chunks %.3f ms, %llu packed chunks %.3f ms -> raw share %.2f\n", (unsigned long long) R,
+						t_raw, (unsigned long long) (n_chunks - R), t_pk, mt->raw_share);
+		}
+	}
+	(void) cudaGetLastError();
 	double secs = 0;
 	for (uint64_t ci = 0; ci < n_chunks; ci++) {
 		float ms = 0;
@@ -603,6 +631,9 @@ int acwm_result_device_ptrs(acwm_matcher *mt, uint64_t **d_count, uint64_t **d_p
 	return ACWM_OK;
 }
 
+static int search_host_raw(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t *count, uint64_t *positions, uint64_t cap,
+		uint64_t *n_written, int want_positions);
+
 int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t *count, uint64_t *positions,
 		uint64_t cap, uint64_t *n_written) {
 	if (!mt || (!text && n))
@@ -616,12 +647,44 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		return rc;
 	const int pack_mode = host_pack_mode();
 	if (mt->c.prm.packed2bit && n >= kHostPackMin && pack_mode > 0) {
-		if (!mt->packer)
-			mt->packer = new HostPacker();
-		// worth it only with enough cores to out-run the link (a core packs 5-7 GB/s, PCIe moves ~50 GB/s of raw text)
-		if (mt->packer->threads() >= kHostPackMinThreads || pack_mode == 2)
+		if (!mt->packer) {
+			try { // thread creation may throw: no exception leaves the C ABI, the text then goes unpacked
+				mt->packer = new HostPacker();
+			} catch (...) {
+				mt->packer = nullptr;
+				return search_host_raw(mt, text, n, count, positions, cap, n_written, want_positions);
+			}
+		}
+		// Packing pays when the cores out-run what the link carries raw (a core packs 5-7 GB/s, one PCIe link moves
+		// ~55 GB/s of raw text) -- and when the box has the memory bandwidth for both: the first search runs the hybrid
+		// transfer, the second the plain copy, and from then on the faster of the two (re-tried every 32nd call).
+		if (pack_mode == 2)
 			return search_host_packed(mt, text, n, count, positions, cap, n_written, want_positions);
+		if (mt->packer->threads() >= kHostPackMinThreads) {
+			int mode = mt->host_calls == 0 ? 1 : mt->host_calls == 1 ? 0 : (mt->host_rate[1] >= mt->host_rate[0] ? 1 : 0);
+			if (mt->host_calls >= 2 && mt->host_calls % 32 == 31)
+				mode ^= 1;
+			timespec t0, t1;
+			clock_gettime(CLOCK_MONOTONIC, &t0);
+			rc = mode ? search_host_packed(mt, text, n, count, positions, cap, n_written, want_positions)
+					  : search_host_raw(mt, text, n, count, positions, cap, n_written, want_positions);
+			clock_gettime(CLOCK_MONOTONIC, &t1);
+			const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+			if ((rc == ACWM_OK || rc == ACWM_ERR_OVERFLOW) && secs > 0) {
+				const double rate = (double) n / secs;
+				mt->host_rate[mode] = mt->host_rate[mode] > 0 ? 0.5 * mt->host_rate[mode] + 0.5 * rate : rate;
+			}
+			mt->host_calls++;
+			return rc;
+		}
 	}
+	return search_host_raw(mt, text, n, count, positions, cap, n_written, want_positions);
+}
+
+// The text crosses the link one byte per symbol: chunks of 32 MiB, copy of chunk i under the scan of chunk i - 1.
+static int search_host_raw(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t *count, uint64_t *positions, uint64_t cap,
+		uint64_t *n_written, int want_positions) {
+	int rc;
 	if (n + 64 > mt->text_cap) {
 		if (mt->d_text)
 			cudaFree(mt->d_text);
@@ -803,6 +866,9 @@ void acwm_free(acwm_matcher *mt) {
 		if (mt->s_copy2)
 			cudaStreamDestroy(mt->s_copy2);
 		for (auto e : mt->ev_pack)
+			if (e)
+				cudaEventDestroy(e);
+		for (auto e : mt->ev_hyb)
 			if (e)
 				cudaEventDestroy(e);
 		if (mt->s_copy)

@@ -58,6 +58,13 @@ struct acwm_matcher {
 	uint64_t raw_cap = 0;
 	cudaStream_t s_copy2 = nullptr;          // its copy stream
 	std::array<cudaEvent_t, 16> ev_pack{};    // one per ring slot: its copy is done
+	std::array<cudaEvent_t, 4> ev_hyb{};      // hybrid transfer: start / end of the raw copies, start / end of the packed copies
+	// acwm_search_host picks between the hybrid (packing) transfer and the plain one-byte-per-symbol copy by what
+	// each DELIVERED on this box (text bytes per second of the whole call): eight ranks that share one box's memory
+	// and PCIe root are served best by the plain copy, a single rank with all cores by the hybrid one
+	double host_rate[2] = {0, 0};             // [0] plain copy, [1] hybrid; 0 = not tried yet
+	uint32_t host_calls = 0;
+	double raw_share = -1;                    // share of a pinned text sent unpacked, adapted from call to call (< 0: not yet measured)
 	std::vector<cudaEvent_t> ev_time;
 	std::array<cudaEvent_t, 2> ev_prof{};
 	bool profiling = false;

@@ -264,6 +264,102 @@ unsigned int search_wu2(unsigned char *pattern, int m, int p_size, unsigned char
 	return search_wu_common(std::vector<uint8_t>(pattern, pattern + (size_t) m * p_size), m, p_size, text, n, SHIFT);
 }
 
+// ------------------------------------------------------------------ sibling algorithms (sh/sh.c, sbom/sbom.c, sog/sog8.c)
+// Set-Horspool, Set Backward Oracle Matching and Shift-Or with q-grams count the same thing as Aho-Corasick and
+// Wu-Manber: the end positions whose window of m symbols is one of the (distinct) patterns.  Behind their entry points
+// sits the same matcher; the caller's flat tables are filled as the reference fills them (tables.cpp).
+struct ac_table *preproc_sh(unsigned char **pattern, int m, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_final) {
+	struct ac_table *table = (struct ac_table *) malloc(sizeof(struct ac_table));
+	if (!table) {
+		fprintf(stderr, "Could not initialize table\n"); // sh/sh.c:172
+		exit(1);
+	}
+	unsigned ns = 0, nd = 0;
+	fill_reference_sh_tables((const uint8_t *const *) pattern, m, p_size, alphabet, state_transition, state_final, &ns, &nd);
+	std::vector<uint8_t> flat = flatten_rows(pattern, m, p_size);
+	table->idcounter = ns;
+	table->patterncounter = nd;
+	table->zerostate = (struct ac_state *) build_or_die(ACWM_ALGO_AC, flat.data(), m, p_size, alphabet, "preproc_sh");
+	return table;
+}
+
+unsigned search_sh(int m, unsigned char *text, int n, struct ac_table *table, int *bmBc) {
+	(void) m, (void) bmBc; // the bad-character shifts steer the reference's skip loop (sh/sh.c:175), not the result
+	return (unsigned) search_or_die((acwm_matcher *) table->zerostate, text, n, "search_sh");
+}
+
+void free_sh(struct ac_table *table, int alphabet) { free_ac(table, alphabet); }
+
+struct sbom_table *preproc_sbom(unsigned char **pattern, int m, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_final_multi) {
+	struct sbom_table *table = (struct sbom_table *) malloc(sizeof(struct sbom_table));
+	if (!table) {
+		fprintf(stderr, "Could not initialize table\n"); // sbom/sbom.c:207
+		exit(1);
+	}
+	unsigned ns = 0, np = 0;
+	fill_reference_sbom_tables((const uint8_t *const *) pattern, m, p_size, alphabet, state_transition, state_final_multi, &ns,
+			&np);
+	std::vector<uint8_t> flat = flatten_rows(pattern, m, p_size);
+	table->idcounter = ns;
+	table->patterncounter = np;
+	table->zerostate = (struct sbom_state *) build_or_die(ACWM_ALGO_AC, flat.data(), m, p_size, alphabet, "preproc_sbom");
+	return table;
+}
+
+unsigned search_sbom(unsigned char **pattern, int m, unsigned char *text, int n, struct sbom_table *table) {
+	(void) pattern, (void) m; // the reference verifies oracle hits against the rows (sbom/sbom.c:178); the matcher owns its copy
+	return (unsigned) search_or_die((acwm_matcher *) table->zerostate, text, n, "search_sbom");
+}
+
+void free_sbom(struct sbom_table *table, int m) {
+	(void) m;
+	if (!table)
+		return;
+	acwm_free((acwm_matcher *) table->zerostate);
+	free(table);
+}
+
+// sog8 has no handle: like the Wu-Manber entry points, the matcher is remembered by the caller's table (T8) and
+// recognised by the patterns.  Patterns are 8 symbols (the reference compares 8 bytes whatever m says, sog8.c:79).
+static uint64_t sog_sig(unsigned char **pattern, int p_size) {
+	uint64_t h = fnv(&p_size, sizeof(p_size));
+	for (int j = 0; j < p_size; j++)
+		h = fnv(pattern[j], 8, h);
+	return h;
+}
+
+void preproc_sog8(uint8_t *T8, uint32_t *scanner_hs, int *scanner_index, uint8_t *scanner_hs2, unsigned char **pattern, int m,
+		unsigned char *text, int n, int p_size, int B) {
+	(void) text, (void) n, (void) B;
+	if (m != 8) {
+		fprintf(stderr, "acwm preproc_sog8: patterns of 8 symbols only (sog/sog8.c:79)\n");
+		exit(1);
+	}
+	fill_reference_sog8_tables((const uint8_t *const *) pattern, p_size, T8, scanner_hs, scanner_index, scanner_hs2);
+	std::vector<uint8_t> flat = flatten_rows(pattern, 8, p_size);
+	remember(T8, build_or_die(ACWM_ALGO_AC, flat.data(), 8, p_size, 256, "preproc_sog8"), sog_sig(pattern, p_size));
+}
+
+unsigned int search_sog8(uint8_t *T8, uint32_t *scanner_hs, int *scanner_index, uint8_t *scanner_hs2, unsigned char **pattern,
+		int m, unsigned char *text, int n, int p_size, int B) {
+	(void) scanner_hs, (void) scanner_index, (void) scanner_hs2, (void) B;
+	if (m != 8) {
+		fprintf(stderr, "acwm search_sog8: patterns of 8 symbols only (sog/sog8.c:79)\n");
+		exit(1);
+	}
+	acwm_matcher *mt = lookup(T8, sog_sig(pattern, p_size));
+	if (!mt) { // preproc_sog8 was not called with this table
+		std::vector<uint8_t> flat = flatten_rows(pattern, 8, p_size);
+		mt = build_or_die(ACWM_ALGO_AC, flat.data(), 8, p_size, 256, "search_sog8");
+		remember(T8, mt, sog_sig(pattern, p_size));
+	}
+	return (unsigned) search_or_die(mt, text, n, "search_sog8");
+}
+
+void acwm_shim_forget(const void *table) { forget(table); }
+
 // ------------------------------------------------------------------ GPU wrappers
 #define ACWM_CUDA_AC(N)                                                                                         \
 	void cuda_ac##N(int m, unsigned char *text, int n, int p_size, int alphabet, int *state_transition,         \

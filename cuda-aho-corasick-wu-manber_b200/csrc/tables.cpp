@@ -756,6 +756,123 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 }
 
 // ------------------------------------------------------------------ reference-layout tables (shims)
+// Set-Horspool (sh/sh.c:78-149): the goto function of the trie of the reversed patterns, ids in creation order,
+// root row zeroed first (sh_init, :58-59), terminal flag where a pattern ends (:131).  The trie is kept privately
+// (flat child array), so what the caller's arrays held before does not matter.
+void fill_reference_sh_tables(const uint8_t *const *rows, int m, int p, int alphabet, int *state_transition,
+		unsigned *state_final, unsigned *n_states, unsigned *n_distinct) {
+	const size_t A = (size_t) alphabet;
+	for (int c = 0; c < alphabet; c++)
+		state_transition[c] = 0;
+	std::vector<int> child(A, -1); // child[state * A + sym]
+	std::vector<uint8_t> is_final(1, 0);
+	unsigned distinct = 0;
+	for (int i = 0; i < p; i++) {
+		int state = 0;
+		for (int j = m - 1; j >= 0; j--) {
+			const unsigned c = rows[i][j];
+			int nx = child[(size_t) state * A + c];
+			if (nx < 0) {
+				nx = (int) is_final.size();
+				is_final.push_back(0);
+				child.resize(child.size() + A, -1);
+				child[(size_t) state * A + c] = nx;
+				state_transition[(size_t) state * A + c] = nx;
+			}
+			state = nx;
+		}
+		if (!is_final[(size_t) state]) {
+			is_final[(size_t) state] = 1;
+			state_final[state] = 1;
+			distinct++;
+		}
+	}
+	if (n_states)
+		*n_states = (unsigned) is_final.size();
+	if (n_distinct)
+		*n_distinct = distinct;
+}
+
+// Set Backward Oracle Matching (sbom/sbom.c:51-150): the factor oracle of the reversed patterns.  A pattern first
+// follows whatever transitions exist -- trie edges AND the extra oracle edges earlier patterns left (:62-70) -- and
+// creates states for the rest; each new state hangs extra edges on the supply chain of its parent (:104-113) and takes
+// its own supply link from where that walk stops (:115-118).  F(q): cell 0 = number of patterns ending in q, cells
+// 1.. = their row numbers (:145-146), 200 cells per state as the reference lays them out.
+void fill_reference_sbom_tables(const uint8_t *const *rows, int m, int p, int alphabet, int *state_transition,
+		unsigned *state_final_multi, unsigned *n_states, unsigned *n_patterns) {
+	const size_t A = (size_t) alphabet;
+	for (int c = 0; c < alphabet; c++)
+		state_transition[c] = 0;
+	std::vector<int> next(A, -1), fail(1, -1);
+	std::vector<unsigned> num(1, 0);
+	for (int i = 0; i < p; i++) {
+		int state = 0, j = m - 1;
+		while (j >= 0) {
+			const int nx = next[(size_t) state * A + rows[i][j]];
+			if (nx < 0)
+				break;
+			state = nx;
+			j--;
+		}
+		for (; j >= 0; j--) {
+			const unsigned c = rows[i][j];
+			const int nx = (int) fail.size();
+			fail.push_back(0);
+			num.push_back(0);
+			next.resize(next.size() + A, -1);
+			state_transition[(size_t) state * A + c] = nx;
+			next[(size_t) state * A + c] = nx;
+			int k = fail[(size_t) state];
+			while (k >= 0 && next[(size_t) k * A + c] < 0) {
+				next[(size_t) k * A + c] = nx;
+				state_transition[(size_t) k * A + c] = nx;
+				k = fail[(size_t) k];
+			}
+			fail[(size_t) nx] = k >= 0 ? next[(size_t) k * A + c] : 0;
+			state = nx;
+		}
+		if (num[(size_t) state] < 199) { // the reference's F(q) holds 200 cells
+			state_final_multi[(size_t) state * 200] = num[(size_t) state] + 1;
+			state_final_multi[(size_t) state * 200 + num[(size_t) state] + 1] = (unsigned) i;
+			num[(size_t) state]++;
+		}
+	}
+	if (n_states)
+		*n_states = (unsigned) fail.size();
+	if (n_patterns)
+		*n_patterns = (unsigned) p;
+}
+
+// Shift-Or with q-grams, 8-symbol patterns (sog/sog8.c:113-170): T8[3-gram] has bit i CLEAR when some pattern holds the
+// 3-gram at offset i (0..5); scanner_hs = the 32-bit hash of each pattern (bytes 0..3 xor bytes 4..7, big endian),
+// sorted, with scanner_index carrying the pattern rows; scanner_hs2 = the bitmap of the 16-bit fold of the hashes.
+// Two places where this cannot be byte-identical: the reference folds an UNINITIALISED variable into the two-level
+// hash (sog8.c:128) -- the fold of the pattern's own hash, which its search computes (:50-51), is stored here -- and
+// its quicksort (:28-47) leaves equal hashes in an order of its own (here: by pattern row).
+void fill_reference_sog8_tables(const uint8_t *const *rows, int p, uint8_t *T8, uint32_t *scanner_hs, int *scanner_index,
+		uint8_t *scanner_hs2) {
+	memset(T8, 0xff, (size_t) 1 << 24);
+	memset(scanner_hs2, 0, 32 * 256);
+	std::vector<std::pair<uint32_t, int>> hs((size_t) p);
+	auto get32 = [](const uint8_t *a) { return ((uint32_t) a[0] << 24) + ((uint32_t) a[1] << 16) + ((uint32_t) a[2] << 8) + a[3]; };
+	for (int i = 0; i < p; i++) {
+		const uint8_t *q = rows[i];
+		const uint32_t h = get32(q) ^ get32(q + 4);
+		hs[(size_t) i] = {h, i};
+		const uint16_t h2 = (uint16_t) ((h >> 16) ^ h);
+		scanner_hs2[h2 >> 3] |= (uint8_t) (1u << (h2 & 7));
+		for (int k = 0; k < 6; k++) {
+			const uint32_t g = (uint32_t) q[k] + ((uint32_t) q[k + 1] << 8) + ((uint32_t) q[k + 2] << 16);
+			T8[g] &= (uint8_t) (0xff - (1u << k));
+		}
+	}
+	std::stable_sort(hs.begin(), hs.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+	for (int i = 0; i < p; i++) {
+		scanner_hs[i] = hs[(size_t) i].first;
+		scanner_index[i] = hs[(size_t) i].second;
+	}
+}
+
 void fill_reference_ac_tables(const uint8_t *const *rows, int m, int p, int alphabet, int *state_transition,
 		unsigned *state_supply, unsigned *state_final, unsigned *n_states, unsigned *n_distinct) {
 	// Same observable content as preproc_ac (ac/ac.c:224-245): root row zeroed first

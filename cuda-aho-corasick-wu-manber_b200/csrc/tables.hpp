@@ -76,6 +76,17 @@ inline uint32_t mix64to32(uint64_t v) {
 // its caller's arrays: ac/ac.c:61-62,114,162,186 and wu/wu.c:109-149).
 void fill_reference_ac_tables(const uint8_t *const *rows, int m, int p, int alphabet, int *state_transition,
 		unsigned *state_supply, unsigned *state_final, unsigned *n_states, unsigned *n_distinct);
+// Sibling algorithms behind the same matcher (same result set for equal-length patterns): the caller's flat tables
+// as the reference's preproc_sh (sh/sh.c:78-149: trie of the REVERSED patterns), preproc_sbom (sbom/sbom.c:51-150:
+// factor oracle of the reversed patterns, supply links resolved while the states are created, F(q) lists of 200
+// cells per state) and preproc_sog8 (sog/sog8.c:113-170: 3-gram position masks, pattern hashes, two-level hash
+// bitmap) leave them.
+void fill_reference_sh_tables(const uint8_t *const *rows, int m, int p, int alphabet, int *state_transition,
+		unsigned *state_final, unsigned *n_states, unsigned *n_distinct);
+void fill_reference_sbom_tables(const uint8_t *const *rows, int m, int p, int alphabet, int *state_transition,
+		unsigned *state_final_multi, unsigned *n_states, unsigned *n_patterns);
+void fill_reference_sog8_tables(const uint8_t *const *rows, int p, uint8_t *T8, uint32_t *scanner_hs, int *scanner_index,
+		uint8_t *scanner_hs2);
 unsigned reference_wu_shiftsize(int alphabet);
 void fill_reference_wu_tables(const uint8_t *const *rows, const uint8_t *flat, int m, int p, int B, int nbits,
 		int *SHIFT, int *PREFIX_value, int *PREFIX_index, int *PREFIX_size);

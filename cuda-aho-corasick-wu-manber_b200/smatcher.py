@@ -23,6 +23,10 @@ class ac_table(C.Structure):  # smatcher.h:49-53
     _fields_ = [("idcounter", C.c_uint), ("patterncounter", C.c_uint), ("zerostate", C.c_void_p)]
 
 
+class sbom_table(C.Structure):  # smatcher.h:65-69
+    _fields_ = [("idcounter", C.c_uint), ("patterncounter", C.c_uint), ("zerostate", C.c_void_p)]
+
+
 _bound = False
 
 
@@ -57,6 +61,26 @@ def _bind():
         g.restype = C.c_int
         g.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_int] + wu_tabs + [C.POINTER(C.c_double)]
     L.acwm_shim_last_count.restype = C.c_ulonglong
+    # sibling algorithms (smatcher.h:93-99,109-110)
+    L.preproc_sh.restype = C.POINTER(ac_table)
+    L.preproc_sh.argtypes = [pp, C.c_int, C.c_int, C.c_int, _i32p, _u32p]
+    L.search_sh.restype = C.c_uint
+    L.search_sh.argtypes = [C.c_int, _u8p, C.c_int, C.POINTER(ac_table), _i32p]
+    L.free_sh.restype = None
+    L.free_sh.argtypes = [C.POINTER(ac_table), C.c_int]
+    L.preproc_sbom.restype = C.POINTER(sbom_table)
+    L.preproc_sbom.argtypes = [pp, C.c_int, C.c_int, C.c_int, _i32p, _u32p]
+    L.search_sbom.restype = C.c_uint
+    L.search_sbom.argtypes = [pp, C.c_int, _u8p, C.c_int, C.POINTER(sbom_table)]
+    L.free_sbom.restype = None
+    L.free_sbom.argtypes = [C.POINTER(sbom_table), C.c_int]
+    sog_tabs = [_u8p, _u32p, _i32p, _u8p]
+    L.preproc_sog8.restype = None
+    L.preproc_sog8.argtypes = sog_tabs + [pp, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
+    L.search_sog8.restype = C.c_uint
+    L.search_sog8.argtypes = sog_tabs + [pp, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
+    L.acwm_shim_forget.restype = None
+    L.acwm_shim_forget.argtypes = [C.c_void_p]
     _bound = True
     return L
 
@@ -135,6 +159,51 @@ def cuda_wm(variant, pattern2, m, text, n, p_size, alphabet, B, SHIFT, PREFIX_va
                                               _p(SHIFT, _i32p), _p(PREFIX_value, _i32p), _p(PREFIX_index, _i32p),
                                               _p(PREFIX_size, _i32p), C.byref(t))
     return int(c), float(t.value)
+
+
+# ---- sibling algorithms: Set-Horspool, SBOM, Shift-Or with q-grams (smatcher.h:93-99,109-110)
+def preproc_sh(pattern, m, p_size, alphabet, state_transition, state_final):
+    return _bind().preproc_sh(_rows(pattern), m, p_size, alphabet, _p(state_transition, _i32p), _p(state_final, _u32p))
+
+
+def search_sh(m, text, n, table, bmBc):
+    return int(_bind().search_sh(m, _p(text, _u8p), n, table, _p(bmBc, _i32p)))
+
+
+def free_sh(table, alphabet):
+    _bind().free_sh(table, alphabet)
+
+
+def preproc_sbom(pattern, m, p_size, alphabet, state_transition, state_final_multi):
+    return _bind().preproc_sbom(_rows(pattern), m, p_size, alphabet, _p(state_transition, _i32p),
+                                _p(state_final_multi, _u32p))
+
+
+def search_sbom(pattern, m, text, n, table):
+    return int(_bind().search_sbom(_rows(pattern), m, _p(text, _u8p), n, table))
+
+
+def free_sbom(table, m):
+    _bind().free_sbom(table, m)
+
+
+def alloc_sog8_tables(p_size):
+    """T8 (2^24 bytes), scanner_hs, scanner_index, scanner_hs2 (8192 bytes): the allocation main.c keeps in comments."""
+    return (np.empty(1 << 24, np.uint8), np.zeros(p_size, np.uint32), np.zeros(p_size, np.int32), np.zeros(8192, np.uint8))
+
+
+def preproc_sog8(T8, scanner_hs, scanner_index, scanner_hs2, pattern, m, text, n, p_size, B=3):
+    _bind().preproc_sog8(_p(T8, _u8p), _p(scanner_hs, _u32p), _p(scanner_index, _i32p), _p(scanner_hs2, _u8p),
+                         _rows(pattern), m, _p(text, _u8p), n, p_size, B)
+
+
+def search_sog8(T8, scanner_hs, scanner_index, scanner_hs2, pattern, m, text, n, p_size, B=3):
+    return int(_bind().search_sog8(_p(T8, _u8p), _p(scanner_hs, _u32p), _p(scanner_index, _i32p), _p(scanner_hs2, _u8p),
+                                   _rows(pattern), m, _p(text, _u8p), n, p_size, B))
+
+
+def shim_forget(table):
+    _bind().acwm_shim_forget(table.ctypes.data)
 
 
 def alloc_ac_tables(m, p_size, alphabet):

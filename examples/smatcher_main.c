@@ -32,7 +32,7 @@
 #include "acwm.h" /* declares the smatcher.h entry points + cuda_acN / cuda_wmN */
 
 static void usage(void) {
-	fprintf(stderr, "usage: smatcher_main <ac|wm> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-data DIR [-c]] [-seed S] [-gpus G]\n");
+	fprintf(stderr, "usage: smatcher_main <ac|wm|sh|sbom> -m M -n N -p_size P -alphabet A [-text FILE -pattern FILE] [-data DIR [-c]] [-seed S] [-gpus G]\n");
 	exit(2);
 }
 
@@ -65,9 +65,10 @@ int main(int argc, char **argv) {
 	int create_data = 0, gpus = 0;
 	unsigned long long seed = 0;
 	static char sel_text[4096], sel_pattern[4096];
-	if (argc < 2 || (strcmp(argv[1], "ac") && strcmp(argv[1], "wm")))
+	if (argc < 2 || (strcmp(argv[1], "ac") && strcmp(argv[1], "wm") && strcmp(argv[1], "sh") && strcmp(argv[1], "sbom")))
 		usage();
-	const int use_ac = strcmp(argv[1], "ac") == 0;
+	const int use_sh = strcmp(argv[1], "sh") == 0, use_sbom = strcmp(argv[1], "sbom") == 0;
+	const int use_ac = strcmp(argv[1], "ac") == 0 || use_sh || use_sbom; /* the siblings run on the automaton matcher */
 	for (i = 2; i + 1 < argc; i++) {
 		if (!strcmp(argv[i], "-m")) m = atoi(argv[i + 1]);
 		if (!strcmp(argv[i], "-n")) n = atoi(argv[i + 1]);
@@ -133,7 +134,43 @@ int main(int argc, char **argv) {
 		memcpy(pattern[j], pattern2 + (size_t) j * m, (size_t) m);
 	}
 
-	if (use_ac) {
+	if (use_sh) {
+		/* multish (main.c:158-195): the caller's tables (main.c:408-427), preprocess, search, free */
+		const size_t states = (size_t) m * p_size + 1;
+		int *state_transition = (int *) malloc(states * alphabet * sizeof(int));
+		unsigned int *state_final = (unsigned int *) calloc(states, sizeof(unsigned int));
+		int *bmBc = (int *) calloc((size_t) alphabet, sizeof(int)); /* preBmBc (main.c:173) steers the CPU skip loop only */
+		memset(state_transition, -1, states * alphabet * sizeof(int));
+		double t = now_s();
+		struct ac_table *table = preproc_sh(pattern, m, p_size, alphabet, state_transition, state_final);
+		const double t_pre = now_s() - t;
+		t = now_s();
+		const unsigned matches = search_sh(m, text, n, table, bmBc);
+		printf("search_sh matches \t%u\t time \t%f\n", matches, now_s() - t);
+		printf("preproc_sh states \t%u\t patterns \t%u\t time \t%f\n", table->idcounter, table->patterncounter, t_pre);
+		printf("Total results: %u.\n", matches);
+		free_sh(table, alphabet);
+		free(state_transition);
+		free(state_final);
+		free(bmBc);
+	} else if (use_sbom) {
+		/* multisbom (main.c:197-233) */
+		const size_t states = (size_t) m * p_size + 1;
+		int *state_transition = (int *) malloc(states * alphabet * sizeof(int));
+		unsigned int *state_final_multi = (unsigned int *) calloc(states * 200, sizeof(unsigned int));
+		memset(state_transition, -1, states * alphabet * sizeof(int));
+		double t = now_s();
+		struct sbom_table *table = preproc_sbom(pattern, m, p_size, alphabet, state_transition, state_final_multi);
+		const double t_pre = now_s() - t;
+		t = now_s();
+		const unsigned matches = search_sbom(pattern, m, text, n, table);
+		printf("search_sbom matches \t%u\t time \t%f\n", matches, now_s() - t);
+		printf("preproc_sbom states \t%u\t patterns \t%u\t time \t%f\n", table->idcounter, table->patterncounter, t_pre);
+		printf("Total results: %u.\n", matches);
+		free_sbom(table, m);
+		free(state_transition);
+		free(state_final_multi);
+	} else if (use_ac) {
 		/* ---- caller-side tables of main.c:408-420 */
 		const size_t states = (size_t) m * p_size + 1;
 		int *state_transition = (int *) malloc(states * alphabet * sizeof(int));

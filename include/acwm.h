@@ -369,6 +369,36 @@ int cuda_wm5(unsigned char *pattern, int m, unsigned char *text, int n, int p_si
 /* Count of the last cuda_acN call (the reference prints it and returns void). */
 unsigned long long acwm_shim_last_count(void);
 
+/* ------------------- sibling algorithms behind the same matcher (smatcher.h:93-99,109-110) -------------------
+ * Set-Horspool (sh/sh.c:151-178), Set Backward Oracle Matching (sbom/sbom.c:152-196) and Shift-Or with q-grams
+ * (sog/sog8.c:97-115) return what search_ac / search_wu return: the number of end positions whose m-symbol window is
+ * one of the distinct patterns.  Same signatures as the reference; the searches run on the GPU through the matcher
+ * compiled by the preproc call.  The caller's flat tables are filled as the reference fills them (state ids in
+ * creation order over the REVERSED patterns, oracle edges and F(q) lists for sbom, 3-gram masks / sorted hashes /
+ * two-level bitmap for sog8 -- see csrc/tables.cpp for the two documented deviations of sog8). */
+struct sbom_state; /* smatcher.h:57-63; never dereferenced by callers of this path */
+struct sbom_table { /* smatcher.h:65-69 */
+	unsigned int idcounter;
+	unsigned int patterncounter;
+	struct sbom_state *zerostate; /* here: opaque pointer to the acwm_matcher */
+};
+struct ac_table *preproc_sh(unsigned char **pattern, int m, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_final);
+unsigned search_sh(int m, unsigned char *text, int n, struct ac_table *table, int *bmBc);
+void free_sh(struct ac_table *table, int alphabet);
+struct sbom_table *preproc_sbom(unsigned char **pattern, int m, int p_size, int alphabet, int *state_transition,
+		unsigned int *state_final_multi);
+unsigned search_sbom(unsigned char **pattern, int m, unsigned char *text, int n, struct sbom_table *table);
+void free_sbom(struct sbom_table *table, int m);
+/* T8: 2^24 bytes, scanner_hs / scanner_index: p_size entries, scanner_hs2: 8192 bytes (main.c:546 and the commented
+ * allocation above it); m must be 8.  The matcher is remembered by T8; acwm_shim_forget(T8) releases it. */
+void preproc_sog8(uint8_t *T8, uint32_t *scanner_hs, int *scanner_index, uint8_t *scanner_hs2, unsigned char **pattern, int m,
+		unsigned char *text, int n, int p_size, int B);
+unsigned int search_sog8(uint8_t *T8, uint32_t *scanner_hs, int *scanner_index, uint8_t *scanner_hs2, unsigned char **pattern,
+		int m, unsigned char *text, int n, int p_size, int B);
+/* Releases the matcher a table-keyed entry point (preproc_wu*, cuda_acN, cuda_wmN, preproc_sog8) remembers for `table`. */
+void acwm_shim_forget(const void *table);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PORT_SO = os.path.join(_HERE, "liboracle_port.so")
 _REF_SO = os.path.join(_HERE, "_ref", "libref_oracle.so")
+_SIB_SO = os.path.join(_HERE, "_ref", "libref_siblings.so")
 
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -107,6 +108,70 @@ def ref():
                                       _i32p, _i32p, _i32p, _i32p, _f64p]
         _ref = lib
     return _ref
+
+
+_sib = None
+
+
+def siblings_available() -> bool:
+    if os.path.exists(_SIB_SO):
+        return True
+    if os.path.isdir("/root/reference/sh"):
+        build()
+        return os.path.exists(_SIB_SO)
+    return False
+
+
+def siblings():
+    """oracle/_ref/libref_siblings.so: the UNMODIFIED reference sh/sh.c + sbom/sbom.c behind ref_siblings.c."""
+    global _sib
+    if _sib is None:
+        if not siblings_available():
+            raise RuntimeError("oracle/_ref/libref_siblings.so missing (build it where /root/reference exists)")
+        lib = C.CDLL(_SIB_SO)
+        for name in ("ref_sh_search", "ref_sbom_search"):
+            f = getattr(lib, name)
+            f.restype = C.c_ulonglong
+            f.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
+        lib.ref_sh_tables.restype = C.c_uint
+        lib.ref_sh_tables.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _i32p, _u32p, _u32p]
+        lib.ref_sbom_tables.restype = C.c_uint
+        lib.ref_sbom_tables.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _i32p, _u32p]
+        _sib = lib
+    return _sib
+
+
+def ref_sh(patterns, alphabet: int, text=None, want_tables: bool = False):
+    """Reference preproc_sh (+ search_sh with the classic bad-character table).  Returns dict."""
+    pats = _as_u8(patterns)
+    p, m = pats.shape
+    out = {}
+    if text is not None:
+        txt = _as_u8(text)
+        out["count"] = int(siblings().ref_sh_search(_ptr(pats, _u8p), m, p, alphabet, _ptr(txt, _u8p), len(txt)))
+    if want_tables:
+        ns = m * p + 1
+        tr, fin, nd = np.empty(ns * alphabet, np.int32), np.empty(ns, np.uint32), np.zeros(1, np.uint32)
+        out["n_states"] = int(siblings().ref_sh_tables(_ptr(pats, _u8p), m, p, alphabet, _ptr(tr, _i32p), _ptr(fin, _u32p),
+                                                       _ptr(nd, _u32p)))
+        out.update(state_transition=tr, state_final=fin, n_distinct=int(nd[0]))
+    return out
+
+
+def ref_sbom(patterns, alphabet: int, text=None, want_tables: bool = False):
+    """Reference preproc_sbom (+ search_sbom).  Returns dict."""
+    pats = _as_u8(patterns)
+    p, m = pats.shape
+    out = {}
+    if text is not None:
+        txt = _as_u8(text)
+        out["count"] = int(siblings().ref_sbom_search(_ptr(pats, _u8p), m, p, alphabet, _ptr(txt, _u8p), len(txt)))
+    if want_tables:
+        ns = m * p + 1
+        tr, fm = np.empty(ns * alphabet, np.int32), np.empty(ns * 200, np.uint32)
+        out["n_states"] = int(siblings().ref_sbom_tables(_ptr(pats, _u8p), m, p, alphabet, _ptr(tr, _i32p), _ptr(fm, _u32p)))
+        out.update(state_transition=tr, state_final_multi=fm)
+    return out
 
 
 # ------------------------------------------------------------------ reference

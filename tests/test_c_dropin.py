@@ -50,6 +50,24 @@ def test_c_driver_prints_oracle_counts(acwm, oracle, tmp_path, idx):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sh", "sbom"])
+def test_c_driver_runs_the_sibling_algorithms(acwm, oracle, tmp_path, name):
+    """argv[1] = sh / sbom (the dispatch main.c:519-531 keeps in comments): multish / multisbom through the shims."""
+    _build(acwm)
+    case = RANDOM_CASES[0]
+    _, algo, alphabet, p, m, n, opts = case
+    pats, text = make_case(case)
+    want = oracle.set_search(pats, text)["count"]
+    tf, pf = tmp_path / "text.bin", tmp_path / "pattern.bin"
+    text.tofile(tf)
+    np.ascontiguousarray(pats).tofile(pf)
+    out = subprocess.run([EXE, name, "-m", str(m), "-n", str(text.size), "-p_size", str(p), "-alphabet", str(alphabet),
+                          "-text", str(tf), "-pattern", str(pf)], capture_output=True, text=True, check=True, timeout=300).stdout
+    assert int(re.search(rf"search_{name} matches \t(\d+)\t", out).group(1)) == want
+    assert int(re.search(r"Total results: (\d+)\.", out).group(1)) == want
+
+
+@pytest.mark.gpu
 def test_c_driver_selects_and_loads_a_corpus(acwm, oracle, tmp_path):
     """-data DIR -c: the corpus is chosen like the reference's select_data_file (n = 4628736 -> text/E.coli2), loaded
     from FASTA through the library's symbol map, the pattern set drawn with hits -- and the printed counts are the
