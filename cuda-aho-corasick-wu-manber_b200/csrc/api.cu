@@ -66,6 +66,7 @@ static int ensure_positions(acwm_matcher *mt, uint64_t cap) {
 	// staging: one reservation block of slack per warp the widest grid can hold
 	// a warp's reservations double in size: at most as many slots idle as it fills, plus its first block
 	mt->stage_cap = 2 * cap + (uint64_t) 2 * kStageBlock * 32 * (uint64_t) std::max(mt->sm_count, 1);
+	mt->host_allocs++;
 	CU(cudaMalloc((void **) &mt->d_staging, kScratchRing * mt->stage_cap * 8)); // one copy per scan in flight (see Work)
 	CU(cudaMalloc((void **) &mt->d_positions, cap * 8));
 	mt->pos_cap = cap;
@@ -80,6 +81,7 @@ static int ensure_tiles(acwm_matcher *mt, uint64_t n_tiles) {
 	mt->d_tile_count = nullptr;
 	mt->tile_cap = 0;
 	const uint64_t want = n_tiles + n_tiles / 8 + 1024;
+	mt->host_allocs++;
 	CU(cudaMalloc((void **) &mt->d_tile_count, kScratchRing * want * 4)); // one copy per scan in flight
 	mt->tile_cap = want;
 	return ACWM_OK;
@@ -175,6 +177,8 @@ static void apply_l2_window(acwm_matcher *mt, cudaStream_t st) {
 	mt->l2_window_stream = (void *) st; // set once per stream, not once per scan
 }
 
+constexpr uint64_t kBigScanBytes = 256ull << 20; // launches of at least this much text: see launch_scan
+
 // Kernel variants that can be switched off for A/B measurements (scripts/tune.py): ACWM_TUNE = OR of
 // 1 (warp-cooperative candidate verification).
 static uint32_t kernel_tune() {
@@ -232,9 +236,19 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 		for (uint32_t r = 0; r < mt->peer_world; r++)
 			a.peers[r] = reinterpret_cast<unsigned long long *>(mt->peer_ptrs[r]);
 	}
-	const uint32_t threads = c.info.threads, warps = threads / 32;
 	const uint64_t ntl = tile_hi - tile_lo;
-	const bool dual = c.info.ctas_per_sm == 2;
+	// Long scans with a verification stage leave the two-half-size-CTAs shape for one full-size CTA per SM: 32 warps
+	// instead of 24 (c2 at 1 GiB per launch: 5.8 against 5.2 TB/s), and what two CTAs per SM hide -- one launch's
+	// prologue and epilogue under its neighbour's scan -- is a few microseconds per launch.  ACWM_BIG_SHAPE=0/1 forces.
+	static const int big_env = [] {
+		const char *e = getenv("ACWM_BIG_SHAPE");
+		return e && *e ? atoi(e) : -1;
+	}();
+	const bool exact = c.prm.algo == ACWM_ALGO_AC && !c.prm.front_kind && c.prm.exact_front;
+	const bool big = c.alt_threads && (big_env >= 0 ? big_env != 0 : (!exact && ntl * kTile >= kBigScanBytes));
+	const uint32_t threads = big ? c.alt_threads : c.info.threads, warps = threads / 32;
+	const uint32_t shape_smem_bytes = big ? c.alt_smem_bytes : c.info.smem_bytes;
+	const bool dual = !big && c.info.ctas_per_sm == 2;
 	const uint32_t sms = (uint32_t) std::max(mt->sm_count, 1);
 	// Overlap mode (device-resident scans only; exchange == "called from acwm_scan_device"): one CTA per SM, launched
 	// as a programmatic dependent launch, so that the CTAs of consecutive scans share the SMs (two half-size CTAs of
@@ -250,10 +264,9 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	grid = (uint32_t) std::max<uint64_t>(1, (ntl + a.tiles_per_cta - 1) / a.tiles_per_cta);
 	// per-tile counts of a span stay in whatever shared memory the tables and the rings leave free
 	const uint32_t smem_max = dual ? kMaxSmemDual : kMaxSmem;
-	a.cnt_cap = (uint32_t) std::min<uint64_t>(a.tiles_per_cta, (smem_max - c.info.smem_bytes) / 4);
-	const uint32_t smem = c.info.smem_bytes + a.cnt_cap * 4;
+	a.cnt_cap = (uint32_t) std::min<uint64_t>(a.tiles_per_cta, (smem_max - shape_smem_bytes) / 4);
+	const uint32_t smem = shape_smem_bytes + a.cnt_cap * 4;
 	{ // the shared-memory layout of scan_kernel.cuh: [1 KiB][per-warp areas][front][offset masks][stage-2 bitmap][per-tile counts]
-		const bool exact = c.prm.algo == ACWM_ALGO_AC && !c.prm.front_kind && c.prm.exact_front;
 		const bool pk_copy = c.prm.packed2bit && !exact;
 		const uint32_t stages = c.prm.packed2bit ? 1u : 2u;
 		const uint32_t front = a.front_in_smem ? ((a.front_bytes + 15u) & ~15u) : 0u;
@@ -333,6 +346,7 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 			cudaFree(mt->d_text);
 		mt->d_text = nullptr;
 		mt->text_cap = 0;
+		mt->host_allocs++;
 		CU(cudaMalloc((void **) &mt->d_text, packed_total + 64));
 		mt->text_cap = packed_total + 64;
 	}
@@ -341,6 +355,7 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 	const uint64_t chunk_tiles = kPackChunk / T, slot_bytes = kPackChunk / 4 + 64;
 	const uint64_t n_chunks = std::max<uint64_t>(1, (n + kPackChunk - 1) / kPackChunk);
 	if (!mt->h_pack_ring) {
+		mt->host_allocs++;
 		CU(cudaMallocHost((void **) &mt->h_pack_ring, kPackRing * slot_bytes));
 		for (auto &e : mt->ev_pack)
 			CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -387,6 +402,7 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 				cudaFree(mt->d_raw);
 			mt->d_raw = nullptr;
 			mt->raw_cap = 0;
+			mt->host_allocs++;
 			CU(cudaMalloc((void **) &mt->d_raw, n_raw + 64));
 			mt->raw_cap = n_raw + 64;
 		}
@@ -656,25 +672,28 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 			}
 		}
 		// Packing pays when the cores out-run what the link carries raw (a core packs 5-7 GB/s, one PCIe link moves
-		// ~55 GB/s of raw text) -- and when the box has the memory bandwidth for both: the first search runs the hybrid
-		// transfer, the second the plain copy, and from then on the faster of the two (re-tried every 32nd call).
+		// ~55 GB/s of raw text) -- and when the box has the memory bandwidth for both: the first searches run the hybrid
+		// transfer, then the plain copy (one call each to set up, one to measure), and from then on the faster of the
+		// two runs (the other is re-tried every 32nd call).
 		if (pack_mode == 2)
 			return search_host_packed(mt, text, n, count, positions, cap, n_written, want_positions);
 		if (mt->packer->threads() >= kHostPackMinThreads) {
-			int mode = mt->host_calls == 0 ? 1 : mt->host_calls == 1 ? 0 : (mt->host_rate[1] >= mt->host_rate[0] ? 1 : 0);
-			if (mt->host_calls >= 2 && mt->host_calls % 32 == 31)
+			// a call that had to allocate (the first of either kind, a longer text) does not count as a measurement
+			int mode = mt->host_rate[1] <= 0 ? 1 : mt->host_rate[0] <= 0 ? 0 : (mt->host_rate[1] >= mt->host_rate[0] ? 1 : 0);
+			if (mt->host_rate[0] > 0 && mt->host_rate[1] > 0 && mt->host_calls % 32 == 31)
 				mode ^= 1;
+			const uint64_t allocs = mt->host_allocs;
 			timespec t0, t1;
 			clock_gettime(CLOCK_MONOTONIC, &t0);
 			rc = mode ? search_host_packed(mt, text, n, count, positions, cap, n_written, want_positions)
 					  : search_host_raw(mt, text, n, count, positions, cap, n_written, want_positions);
 			clock_gettime(CLOCK_MONOTONIC, &t1);
 			const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
-			if ((rc == ACWM_OK || rc == ACWM_ERR_OVERFLOW) && secs > 0) {
+			if ((rc == ACWM_OK || rc == ACWM_ERR_OVERFLOW) && secs > 0 && mt->host_allocs == allocs) {
 				const double rate = (double) n / secs;
 				mt->host_rate[mode] = mt->host_rate[mode] > 0 ? 0.5 * mt->host_rate[mode] + 0.5 * rate : rate;
+				mt->host_calls++;
 			}
-			mt->host_calls++;
 			return rc;
 		}
 	}
@@ -690,6 +709,7 @@ static int search_host_raw(acwm_matcher *mt, const uint8_t *text, uint64_t n, ui
 			cudaFree(mt->d_text);
 		mt->d_text = nullptr;
 		mt->text_cap = 0;
+		mt->host_allocs++;
 		CU(cudaMalloc((void **) &mt->d_text, n + 64));
 		mt->text_cap = n + 64;
 	}

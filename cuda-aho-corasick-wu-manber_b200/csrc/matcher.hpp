@@ -63,7 +63,8 @@ struct acwm_matcher {
 	// each DELIVERED on this box (text bytes per second of the whole call): eight ranks that share one box's memory
 	// and PCIe root are served best by the plain copy, a single rank with all cores by the hybrid one
 	double host_rate[2] = {0, 0};             // [0] plain copy, [1] hybrid; 0 = not tried yet
-	uint32_t host_calls = 0;
+	uint32_t host_calls = 0;                  // measured calls
+	uint64_t host_allocs = 0;                 // device / pinned allocations made by the host-text paths (a call that allocates is not a measurement)
 	double raw_share = -1;                    // share of a pinned text sent unpacked, adapted from call to call (< 0: not yet measured)
 	std::vector<cudaEvent_t> ev_time;
 	std::array<cudaEvent_t, 2> ev_prof{};

@@ -366,7 +366,11 @@ static int compile_ac_packed(const PatternSet &ps, const acwm_options &opts, uin
 			if (rc != ACWM_OK)
 				return rc;
 			prm.front_kind = 1;
-			prm.verify_kind = build_verify_dfa(ps, 4, nullptr, c) ? 1 : 0; // too large for a table: the buckets decide
+			// What decides a candidate window: the exact compare of the hash buckets.  A walk of the full-depth automaton
+			// (ACWM_VERIFY_DFA=1) gives the same answer in m DEPENDENT lookups from L2 -- ~10 us for one lane at m = 32,
+			// and a random text of 128 MiB holds hundreds of windows that share their last 16 symbols with one of
+			// 100 000 patterns: the stragglers cost a quarter of the scan (profiles/README.md, session l).
+			prm.verify_kind = (getenv("ACWM_VERIFY_DFA") && atoi(getenv("ACWM_VERIFY_DFA")) && build_verify_dfa(ps, 4, nullptr, c)) ? 1 : 0;
 			return ACWM_OK;
 		}
 	}
@@ -748,8 +752,15 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 	inf.ctas_per_sm = shape.ctas;
 	inf.front_kind = prm.front_kind;
 	inf.smem_bytes = shape_smem(smem_tables16(out), shape, pk_copy);
-	if (shape.ctas == 2) // never three CTAs on an SM: the bound on scans in flight (Work, scan_common.cuh) rests on it
+	if (shape.ctas == 2) { // never three CTAs on an SM: the bound on scans in flight (Work, scan_common.cuh) rests on it
 		inf.smem_bytes = std::max(inf.smem_bytes, kMinSmemDual);
+		// the same tables under one full-size CTA per SM: the shape of long scans with a verification stage (api.cu)
+		const LaunchShape single = shape_for_tables(smem_tables16(out), packed, pk_copy, false);
+		if (single.warps > shape.warps && !forced_shape && opts.force_ctas != 2) {
+			out.alt_threads = single.warps * 32;
+			out.alt_smem_bytes = shape_smem(smem_tables16(out), single, pk_copy);
+		}
+	}
 	inf.table_bytes = out.front.size() + out.rmask.size() + out.filter2.size() * 4 + out.bucket_start.size() * 4
 			+ out.entries.size() * sizeof(acwm_ventry) + ps.bytes.size() + out.vdfa.size() * 4;
 	return ACWM_OK;

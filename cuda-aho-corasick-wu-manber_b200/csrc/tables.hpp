@@ -41,6 +41,10 @@ struct Compiled {
 	std::vector<uint8_t> symclass;       // bytes-path AC: 256 entries
 	std::vector<uint32_t> vdfa;          // filtered AC: full-depth one-symbol DFA that decides candidate windows
 	uint32_t front_entry_bytes = 2;
+	// a second launch shape for the same tables (0 = none): one full-size CTA per SM where info names two half-size
+	// ones.  Scans with a verification stage run faster that way on long texts (more warps per SM; per-launch
+	// prologue and epilogue no longer matter there), api.cu picks per launch.
+	uint32_t alt_threads = 0, alt_smem_bytes = 0;
 };
 
 // Geometry shared by the builder's cost model and the kernels.

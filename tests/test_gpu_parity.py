@@ -37,6 +37,18 @@ def test_random_cases_match_oracle(acwm, oracle, torch_cuda, case):
     _check(acwm, oracle, algo, pats, alphabet, text, **opts).close()
 
 
+@pytest.mark.parametrize("case", [c for c in RANDOM_CASES if c[6].get("force_front") == 2], ids=lambda c: c[0])
+def test_filtered_ac_with_the_automaton_as_verifier(acwm, oracle, torch_cuda, case, monkeypatch):
+    """ACWM_VERIFY_DFA=1: candidate windows of the filtered AC are decided by a walk of the full-depth automaton
+    (verify_dfa) instead of the bucket compare -- same matches."""
+    monkeypatch.setenv("ACWM_VERIFY_DFA", "1")
+    name, algo, alphabet, p, m, n, opts = case
+    pats, text = make_case(case)
+    mt = _check(acwm, oracle, algo, pats, alphabet, text, **opts)
+    assert mt.params().verify_kind == 1
+    mt.close()
+
+
 @pytest.mark.parametrize("name", sorted(GOLD))
 @pytest.mark.parametrize("algo_name", ["AC", "WM"])
 def test_golden_vectors(acwm, torch_cuda, name, algo_name):

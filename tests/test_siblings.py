@@ -38,6 +38,14 @@ def make_case(alphabet, m, p, n, seed):
     return text, np.ascontiguousarray(pats)
 
 
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
 needs_ref = pytest.mark.skipif(not oracle.siblings_available(), reason="oracle/_ref/libref_siblings.so not built")
 
 
