@@ -24,6 +24,7 @@ cudaError_t launch_scan_packed(const ScanArgs &a, uint32_t threads, uint32_t sme
 cudaError_t launch_scan_bytes(const ScanArgs &a, uint32_t threads, uint32_t smem, uint32_t grid, cudaStream_t st);
 
 constexpr uint64_t kBounceEntries = 8192; // positions fetched together with the result block
+constexpr uint64_t kBounceSlot = 1ull << 17; // positions per pinned slot of the pipelined fetch of a long result (1 MiB)
 
 static thread_local std::string g_last_error;
 
@@ -268,7 +269,7 @@ static int launch_scan(acwm_matcher *mt, const uint8_t *d_text, uint64_t n, uint
 	const uint32_t smem = shape_smem_bytes + a.cnt_cap * 4;
 	{ // the shared-memory layout of scan_kernel.cuh: [1 KiB][per-warp areas][front][offset masks][stage-2 bitmap][per-tile counts]
 		const bool pk_copy = c.prm.packed2bit && !exact;
-		const uint32_t stages = c.prm.packed2bit ? 1u : 2u;
+		const uint32_t stages = c.prm.packed2bit ? 1u : c.info.stages;
 		const uint32_t front = a.front_in_smem ? ((a.front_bytes + 15u) & ~15u) : 0u;
 		const uint32_t rm = (exact || !c.prm.r_in_smem) ? 0u : ((c.prm.r_entries * c.prm.r_entry_bytes + 15u) & ~15u);
 		const uint32_t f2 = (exact || !c.prm.f2_in_smem) ? 0u : ((c.prm.f2_words * 4u + 15u) & ~15u);
@@ -478,6 +479,8 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		float t_raw = 0, t_pk = 0;
 		if (cudaEventElapsedTime(&t_raw, mt->ev_hyb[0], mt->ev_hyb[1]) == cudaSuccess
 				&& cudaEventElapsedTime(&t_pk, mt->ev_hyb[2], mt->ev_hyb[3]) == cudaSuccess && t_raw > 0 && t_pk > 0) {
+			// the packed side is not done before its last chunk is packed and issued: the issue loop on the host clock
+			t_pk = std::max(t_pk, (float) ((t_issue - t_begin) * 1e3));
 			const double a = t_raw / (double) R, b = t_pk / (double) (n_chunks - R);
 			const double target = b / (a + b);
 			const double cur = (double) R / (double) n_chunks;
@@ -622,8 +625,41 @@ int acwm_fetch(acwm_matcher *mt, uint64_t *count, uint64_t *positions, uint64_t 
 		const uint64_t have_b = std::min(w, spec);
 		if (have_b)
 			memcpy(positions, mt->h_bounce, have_b * 8);
-		if (w > have_b)
-			CU(cudaMemcpy(positions + have_b, mt->d_positions + have_b, (w - have_b) * 8, cudaMemcpyDeviceToHost));
+		if (w > have_b) {
+			// the rest: straight into pinned caller memory, else through two pinned 1 MiB slots (copy of slot k + 1 under
+			// the memcpy of slot k) -- a plain cudaMemcpy into pageable memory moves 2-3 GB/s, this 20+
+			cudaPointerAttributes at;
+			const bool pinned_dst = cudaPointerGetAttributes(&at, positions) == cudaSuccess && at.type == cudaMemoryTypeHost;
+			(void) cudaGetLastError();
+			if (pinned_dst) {
+				CU(cudaMemcpyAsync(positions + have_b, mt->d_positions + have_b, (w - have_b) * 8, cudaMemcpyDeviceToHost, st));
+				CU(cudaStreamSynchronize(st));
+			} else {
+				if (!mt->h_bounce2) {
+					mt->host_allocs++;
+					CU(cudaMallocHost((void **) &mt->h_bounce2, 2 * kBounceSlot * 8));
+					for (auto &e : mt->ev_bounce)
+						CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+				}
+				uint64_t issued = have_b, copied = have_b;
+				unsigned k_issue = 0, k_copy = 0;
+				while (copied < w) {
+					while (issued < w && k_issue < k_copy + 2) { // keep both slots busy
+						const uint64_t cnt = std::min<uint64_t>(kBounceSlot, w - issued);
+						CU(cudaMemcpyAsync(mt->h_bounce2 + (k_issue & 1) * kBounceSlot, mt->d_positions + issued, cnt * 8,
+								cudaMemcpyDeviceToHost, st));
+						CU(cudaEventRecord(mt->ev_bounce[k_issue & 1], st));
+						issued += cnt;
+						k_issue++;
+					}
+					const uint64_t cnt = std::min<uint64_t>(kBounceSlot, w - copied);
+					CU(cudaEventSynchronize(mt->ev_bounce[k_copy & 1]));
+					memcpy(positions + copied, mt->h_bounce2 + (k_copy & 1) * kBounceSlot, cnt * 8);
+					copied += cnt;
+					k_copy++;
+				}
+			}
+		}
 		if (dbg) {
 			clock_gettime(CLOCK_MONOTONIC, &ts0);
 			fprintf(stderr, "  acwm_fetch: %llu positions after another %.3f ms\n", (unsigned long long) w,
@@ -891,6 +927,11 @@ void acwm_free(acwm_matcher *mt) {
 		for (auto e : mt->ev_hyb)
 			if (e)
 				cudaEventDestroy(e);
+		for (auto e : mt->ev_bounce)
+			if (e)
+				cudaEventDestroy(e);
+		if (mt->h_bounce2)
+			cudaFreeHost(mt->h_bounce2);
 		if (mt->s_copy)
 			cudaStreamDestroy(mt->s_copy);
 		if (mt->s_scan)

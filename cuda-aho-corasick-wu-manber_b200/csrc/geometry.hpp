@@ -53,7 +53,10 @@ struct LaunchShape {
 };
 constexpr LaunchShape kShapesPacked[] = {{32, 1, 1}, {24, 1, 1}, {16, 1, 1}, {12, 1, 1}, {8, 1, 1}, {4, 1, 1}};
 constexpr LaunchShape kShapesPackedDual[] = {{16, 1, 2}, {12, 1, 2}};
-constexpr LaunchShape kShapesBytes[] = {{16, 2, 1}, {12, 2, 1}, {8, 2, 1}, {4, 2, 1}};
+// bytes path: two raw slots per warp while 16 warps fit beside the tables; else one slot per warp and 20-24 warps
+// (the load of a warp's next tile is then covered by the other warps instead of its own second slot: BASELINE
+// configs[3], 128 KB of tables, runs 20 warps x 1 slot against 12 x 2)
+constexpr LaunchShape kShapesBytes[] = {{16, 2, 1}, {24, 1, 1}, {20, 1, 1}, {12, 2, 1}, {16, 1, 1}, {8, 2, 1}, {4, 2, 1}};
 
 inline uint32_t shape_smem(uint32_t table_bytes, LaunchShape s, bool pk_copy) {
 	return table_bytes + s.warps * warp_smem_bytes(s.stages, pk_copy) + kSmemReserve;

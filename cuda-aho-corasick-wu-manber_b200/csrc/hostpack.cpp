@@ -70,10 +70,48 @@ __attribute__((target("bmi2"))) uint64_t pack_bmi2(const uint8_t *src, uint8_t *
 }
 #endif
 
+#if defined(__x86_64__)
+// AVX-512: 64 symbols -> 16 bytes in three instructions (VPMADDUBSW pairs the symbols: b0 + 4 b1; VPMADDWD pairs the
+// pairs: + 16 (b2 + 4 b3) = one byte per four symbols in every 32-bit lane; VPMOVDB narrows the lanes), against eight PEXT
+// and their shifts; the packed bytes leave with non-temporal stores when the destination allows (the pinned ring is read by
+// the DMA engine only: no read-for-ownership of lines the cores never look at again).
+__attribute__((target("avx512f,avx512bw,avx512vl"))) uint64_t pack_avx512(const uint8_t *src, uint8_t *dst, uint64_t n_sym) {
+	const __m512i w1 = _mm512_set1_epi16(0x0401), w2 = _mm512_set1_epi32(0x00100001);
+	__m512i acc = _mm512_setzero_si512();
+	uint64_t i = 0;
+	const bool stream = (((uintptr_t) dst) & 63) == 0;
+	for (; i + 256 <= n_sym; i += 256) { // 256 symbols -> one 64-byte line
+		__m128i q[4];
+		for (int k = 0; k < 4; k++) {
+			const __m512i x = _mm512_loadu_si512((const void *) (src + i + 64 * k));
+			acc = _mm512_or_si512(acc, x);
+			q[k] = _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(x, w1), w2));
+		}
+		const __m512i line = _mm512_inserti32x4(_mm512_inserti32x4(_mm512_inserti32x4(_mm512_castsi128_si512(q[0]), q[1], 1), q[2], 2), q[3], 3);
+		if (stream)
+			_mm512_stream_si512((__m512i *) (dst + i / 4), line);
+		else
+			_mm512_storeu_si512((void *) (dst + i / 4), line);
+	}
+	if (stream)
+		_mm_sfence();
+	uint64_t bad = (uint64_t) _mm512_reduce_or_epi64(acc);
+	if (i < n_sym)
+		bad |= pack_bmi2(src + i, dst + i / 4, n_sym - i);
+	return bad;
+}
+#endif
+
 using PackFn = uint64_t (*)(const uint8_t *, uint8_t *, uint64_t);
 PackFn pick_pack() {
 #if defined(__x86_64__)
-	if (__builtin_cpu_supports("bmi2"))
+	const char *e = getenv("ACWM_PACK_IMPL"); // generic | bmi2 | avx512 (measurements; default: the best the CPU has)
+	if (e && !strcmp(e, "generic"))
+		return pack_generic;
+	const bool bmi2 = __builtin_cpu_supports("bmi2");
+	if (bmi2 && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") && !(e && !strcmp(e, "bmi2")))
+		return pack_avx512;
+	if (bmi2)
 		return pack_bmi2;
 #endif
 	return pack_generic;

@@ -58,6 +58,8 @@ struct acwm_matcher {
 	uint64_t raw_cap = 0;
 	cudaStream_t s_copy2 = nullptr;          // its copy stream
 	std::array<cudaEvent_t, 16> ev_pack{};    // one per ring slot: its copy is done
+	uint64_t *h_bounce2 = nullptr;            // pinned: two slots of the pipelined fetch of a long position list
+	std::array<cudaEvent_t, 2> ev_bounce{};
 	std::array<cudaEvent_t, 4> ev_hyb{};      // hybrid transfer: start / end of the raw copies, start / end of the packed copies
 	// acwm_search_host picks between the hybrid (packing) transfer and the plain one-byte-per-symbol copy by what
 	// each DELIVERED on this box (text bytes per second of the whole call): eight ranks that share one box's memory

@@ -47,6 +47,8 @@ constexpr unsigned long long kLookbackTimeoutNs = 2000ull * 1000 * 1000; // a pr
 // Work.bad_text bits: 1 = text byte >= 4 on the 2-bit path, 4 = a warp's reservation log overflowed (reported as overflow)
 // ScanArgs.tune bits
 constexpr uint32_t kTuneCoopVerify = 1u;       // candidates of a tile may be checked cooperatively (compacted list, lane i checks candidate i)
+constexpr uint32_t kTuneFaultHideTotal = 2u;    // fault injection (tests only): CTA 0 never publishes its span total and the look-back
+                                               // gives up after 20 ms instead of 2 s -- the path a stuck predecessor would take
 constexpr uint32_t kTuneLaneLocalDefault = 3;  // ... when the warp has more than this many (bits 8..15 of tune); fewer: every lane checks its own
 
 constexpr uint32_t kWorkRing = 4, kScratchRing = 3;

@@ -79,7 +79,7 @@ __device__ __forceinline__ bool tile_is_interior(const ScanArgs &a, uint64_t til
 	return tile >= 1 && (tile + 1) * (uint64_t) kTile <= (a.data_hi & ~(uint64_t) 15);
 }
 
-template <class Front, bool EXACT, int THREADS, int MINB>
+template <class Front, bool EXACT, int THREADS, int MINB, int STAGES = Front::kPacked ? 1 : 2>
 __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_constant__ ScanArgs a) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	constexpr uint32_t W = THREADS / 32;
@@ -93,9 +93,11 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	// The tables behind the front table start where the host says (ScanArgs.s_rmask .. s_cnt: one constant-bank
 	// read each).  Both checked here, loudly.
 	constexpr uint32_t sb = kDynSmemBase;
-	constexpr uint32_t stages = kPacked ? 1u : 2u;
+	constexpr uint32_t stages = STAGES;
+	static_assert(!kPacked || STAGES == 1, "the 2-bit path has one slot per warp");
 	// ring depth of the per-warp tile pipeline: the 2-bit path copies a tile into registers and re-arms its ONE slot
-	// while it walks; the bytes path walks the raw tile in place and loads the next one into its second slot
+	// while it walks; the bytes path walks the raw tile in place and either loads the next one into a second slot
+	// meanwhile (12-16 warps per SM) or has one slot per warp and more warps to cover the load (20 warps)
 	constexpr uint32_t s_warps = sb + kSmemReserve;
 	constexpr uint32_t s_front = s_warps + W * warp_smem_bytes(stages, kPk);
 	const uint32_t tab_bar = sb;
@@ -484,11 +486,13 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 			if constexpr (EXACT)
 				__syncwarp();
 			refill(0);
+			if constexpr (stages > 1) {
 			const uint32_t ti = slot_idx[0], tp = slot_phase[0], tb = slot_buf[0], tr = slot_bar[0];
 			slot_idx[0] = slot_idx[stages - 1], slot_phase[0] = slot_phase[stages - 1];
 			slot_buf[0] = slot_buf[stages - 1], slot_bar[0] = slot_bar[stages - 1];
 			slot_idx[stages - 1] = ti, slot_phase[stages - 1] = tp;
 			slot_buf[stages - 1] = tb, slot_bar[stages - 1] = tr;
+			}
 		}
 	}
 	if (a.trace && lane == 0)
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	};
 	const unsigned long long tag = (unsigned long long) ((a.epoch + 1u) & 0xffffffu) << kTotalShift;
 	if (threadIdx.x == 0) {
-		if (a.want_positions)
+		if (a.want_positions && !((a.tune & kTuneFaultHideTotal) && blockIdx.x == 0))
 			__stcg(a.cta_total + blockIdx.x, tag | my_total); // one 8-byte word: tag and value arrive together
 		trace_mark(a, 5);
 		// overlap mode: from here on we touch what the previous scan of the stream publishes (result block,
@@ -631,7 +635,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 			unsigned long long v;
 			uint32_t spins = 0;
 			while (((v = ld_acquire_u64(a.cta_total + j)) & ~kTotalMask) != tag) {
-				if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > kLookbackTimeoutNs) {
+				if ((++spins & 1023u) == 0
+						&& globaltimer_ns() - t0 > ((a.tune & kTuneFaultHideTotal) ? 20ull * 1000 * 1000 : kLookbackTimeoutNs)) {
 					stalled = true;
 					break;
 				}
@@ -692,9 +697,9 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------ launch helper
-template <class Front, bool EXACT, int THREADS, int MINB>
+template <class Front, bool EXACT, int THREADS, int MINB, int STAGES = Front::kPacked ? 1 : 2>
 static cudaError_t launch_shape(const ScanArgs &a, uint32_t smem, uint32_t grid, cudaStream_t st) {
-	auto kern = scan_kernel<Front, EXACT, THREADS, MINB>;
+	auto kern = scan_kernel<Front, EXACT, THREADS, MINB, STAGES>;
 	static std::atomic<bool> attr_set[64]; // per device; shard threads of one process launch concurrently
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
@@ -742,6 +747,13 @@ static cudaError_t launch_front(const ScanArgs &a, uint32_t threads, uint32_t sm
 		case 384: return launch_shape<Front, EXACT, 384, 2>(a, smem, grid, st);
 		case 256: return launch_shape<Front, EXACT, 256, 2>(a, smem, grid, st);
 		case 128: return launch_shape<Front, EXACT, 128, 2>(a, smem, grid, st);
+		default: return cudaErrorInvalidValue;
+		}
+	} else if (a.stages == 1) { // one raw slot per warp, more warps
+		switch (threads) {
+		case 768: return launch_shape<Front, EXACT, 768, 1, 1>(a, smem, grid, st);
+		case 640: return launch_shape<Front, EXACT, 640, 1, 1>(a, smem, grid, st);
+		case 512: return launch_shape<Front, EXACT, 512, 1, 1>(a, smem, grid, st);
 		default: return cudaErrorInvalidValue;
 		}
 	} else {

@@ -717,10 +717,13 @@ int compile_tables(int algo, const PatternSet &ps, const acwm_options &opts, Com
 	if (forced_shape) { // tuning / tests
 		LaunchShape want{opts.force_threads ? opts.force_threads / 32 : shape.warps,
 				opts.force_stages ? opts.force_stages : shape.stages, opts.force_ctas == 2 ? 2u : 1u};
-		const bool ok = (want.warps == 32 || want.warps == 24 || want.warps == 16 || want.warps == 12 || want.warps == 8
-								|| want.warps == 4)
-				&& want.warps * 32 == (opts.force_threads ? opts.force_threads : want.warps * 32)
-				&& want.stages == (packed ? 1u : 2u) // the ring depth is a compile-time constant of the kernels
+		// the kernels that exist (launch_front, scan_kernel.cuh): 2-bit path 1 slot per warp; bytes path 2 slots with
+		// 4..16 warps or 1 slot with 16..24 warps
+		const uint32_t w = want.warps;
+		const bool kernel_exists = packed ? (want.stages == 1 && (w == 32 || w == 24 || w == 16 || w == 12 || w == 8 || w == 4))
+				: want.stages == 2 ? (w == 16 || w == 12 || w == 8 || w == 4)
+								   : (want.stages == 1 && (w == 24 || w == 20 || w == 16));
+		const bool ok = kernel_exists && want.warps * 32 == (opts.force_threads ? opts.force_threads : want.warps * 32)
 				&& (want.ctas == 1 || (packed && (want.warps == 16 || want.warps == 12)))
 				&& shape_fits(smem_tables16(out), want, pk_copy);
 		if (!ok) {

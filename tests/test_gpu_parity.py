@@ -624,3 +624,35 @@ def test_multi_gib_text_positions_beyond_32_bits(acwm, torch_cuda):
         res.append(pos)
         mt.close()
     assert np.array_equal(res[0], res[1])
+
+
+def test_lookback_timeout_is_reported_not_hung(acwm, torch_cuda, tmp_path):
+    """The span look-back of the position ordering waits for the totals of the spans in front of it; a predecessor that
+    never publishes (fault injected through ACWM_TUNE bit 1: CTA 0 hides its total, the wait is cut to 20 ms) must end
+    in an error from acwm_fetch -- count still exact -- and not in a hung stream.  Own process: the library reads
+    ACWM_TUNE once."""
+    import subprocess
+    import sys
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np, torch, acwm_pkg
+acwm = acwm_pkg.load(); dg = acwm_pkg.submodule("datagen")
+n = 8 << 20
+text = dg.text_host(n, 4, 1)
+pats = dg.patterns_with_hits(text, 100, 8, 4, 2)
+mt = acwm.Matcher(acwm.AC, pats, 4)
+mt.upload(pos_capacity=n)
+d = torch.from_numpy(text).cuda()
+mt.scan_tensor(d)
+try:
+    mt.fetch(cap=n, stream=torch.cuda.current_stream().cuda_stream)
+    print("NO ERROR")
+except acwm.AcwmError as e:
+    print("ERROR", e.code, str(e))
+torch.cuda.synchronize()
+print("DONE")
+""" % (str(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))),)
+    env = dict(__import__("os").environ, ACWM_TUNE="0x0303")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env).stdout
+    assert "DONE" in out and "ERROR %d" % acwm.ERR_CUDA in out and "position ordering gave up" in out, out
