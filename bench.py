@@ -259,21 +259,22 @@ def pin_rank_to_cores(local_rank, local_world):
     return {"pinned": True, "numa_node": node, "cores": len(mine), "first_core": mine[0]}
 
 
-def measure_pinned_copy(torch, dev, nbytes=256 << 20):
+def measure_pinned_copy(torch, dev, nbytes=128 << 20, window_s=0.3):
     """The box's own H2D rate for this rank's link (pinned host -> HBM, cudaMemcpyAsync): the ceiling of e2e when the
-    text crosses the link one byte per symbol."""
+    text crosses the link one byte per symbol.  Every rank copies for the same wall-clock window (the caller lines them
+    up with a barrier), so each figure is the rate with ALL links busy."""
     src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     src.zero_()
     dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     dst.copy_(src, non_blocking=True)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(6):
+    t0 = time.perf_counter()
+    copies = 0
+    while time.perf_counter() - t0 < window_s:
         dst.copy_(src, non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    return 6 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        torch.cuda.synchronize()
+        copies += 1
+    return copies * nbytes / (time.perf_counter() - t0) / 1e9
 
 
 class Rig:
@@ -457,6 +458,8 @@ def run_leg(rig, wl, n, steps, warmup, full=True, pats=None):
         return rep
 
     # ---- end to end through the public API: pinned host text -> count + positions on the host
+    if not host_texts:  # a text generated on the device (larger than 256 MiB): its host copy is the e2e input
+        host_texts = [dev_texts[0].cpu().numpy()]
     pinned = [torch.from_numpy(t).pin_memory() for t in host_texts[:2]]
     if len(pinned) == 1:
         pinned = pinned * 2
