@@ -465,7 +465,7 @@ def run_leg(rig, wl, n, steps, warmup, full=True, pats=None):
         pinned = pinned * 2
     e2e_steps = max(3, min(steps, 10))
     pos_out = np.empty(pos_cap, np.uint64)  # the caller's position buffer, reused
-    for i in range(5):  # acwm_search_host sets up and measures its two transfers on its first four calls
+    for i in range(9):  # acwm_search_host sets up and measures its two transfers and the neighbours of its raw share first
         mt.search_host(pinned[i % 2], out=pos_out)
     rig.barrier()
     t0 = time.perf_counter()

@@ -314,17 +314,20 @@ constexpr uint64_t kPackChunk = 56 * HostPacker::kPieceSymbols; // 14 Mi symbols
 constexpr unsigned kPackRing = 16;
 static_assert(kPackChunk % kTile == 0 && kPackChunk % 64 == 0, "chunks are whole tiles and whole 16-byte pieces");
 // Share of a pinned host text that is sent unpacked beside the packed rest.  ACWM_HOST_RAW_PERCENT fixes it
-// (0 = none).  Otherwise the FIRST search of a matcher takes it from the packer's thread count: link time
-// n(r + (1-r)/4)/L and packing time n(1-r)/P meet at r = (1/P - 1/4L) / (3/4L + 1/P), with P = 5.2 GB/s per packer
-// thread on text that comes from DRAM and L = 56 GB/s for the link (fit on a 16-core box, profiles/README.md session
-// q) -- and every search then MEASURES both sides (events around the raw copies and around the packed copies) and
-// moves the share towards the point where they take equally long.  What the link and the cores really deliver
-// depends on who else uses them (eight ranks of one box share its cores, its memory and its PCIe root), so the
-// share follows the box instead of a model of it.
+// (0 = none).  Otherwise the FIRST search of a matcher takes it from the packer's thread count: both transfers share the
+// link, so link time n(r + (1-r)/4)/L and packing time n(1-r)/P meet at r = (1/P - 1/4L) / (3/4L + 1/P), with P = 5.2 GB/s
+// per packer thread on text that comes from DRAM (9 with the AVX-512 inner loop) and L = 56 GB/s for the link -- and from
+// then on the share CLIMBS on what the calls measure: every search records its own duration (setup excluded) under the
+// number of raw chunks it ran with; the next one runs with the best number so far, or with a neighbour of it that has no
+// figure yet (every 16th call re-tries a neighbour).  What the link and the cores really deliver depends
+// on who else uses them (the ranks of one box share its cores, its memory and its PCIe root), so the share follows the
+// box instead of a model of it.
+constexpr double kMaxRawShare = 0.6;
 static double host_raw_share_model(unsigned threads) {
-	const double P = 5.2 * std::max(1u, threads), L = 56.0;
+	const double per_thread = __builtin_cpu_supports("avx512bw") ? 9.0 : 5.2;
+	const double P = per_thread * std::max(1u, threads), L = 56.0;
 	const double r = (1.0 / P - 0.25 / L) / (0.75 / L + 1.0 / P);
-	return std::min(0.6, std::max(0.1, r));
+	return std::min(kMaxRawShare, std::max(0.0, r));
 }
 static int host_raw_percent_env() {
 	const char *e = getenv("ACWM_HOST_RAW_PERCENT");
@@ -389,11 +392,25 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 	uint64_t R = 0;
 	const uint32_t H = (std::max<uint32_t>(64u, mt->c.prm.m_max) + 63u) & ~63u;
 	const int raw_env = host_raw_percent_env();
-	const double raw_share = raw_env >= 0 ? raw_env / 100.0 : (mt->raw_share >= 0 ? mt->raw_share : host_raw_share_model(mt->packer->threads()));
-	if (n_chunks >= 5 && H <= 4096 && raw_share > 0) {
+	const uint64_t r_max = std::min<uint64_t>({n_chunks - 1, (uint64_t) (n_chunks * kMaxRawShare), (uint64_t) acwm_matcher::kRawTimes - 1});
+	bool climbing = false;
+	if (n_chunks >= 5 && H <= 4096) {
 		cudaPointerAttributes at;
-		if (cudaPointerGetAttributes(&at, text) == cudaSuccess && at.type == cudaMemoryTypeHost)
-			R = std::min<uint64_t>(n_chunks - 1, (uint64_t) (n_chunks * raw_share + 0.5));
+		if (cudaPointerGetAttributes(&at, text) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+			if (raw_env >= 0)
+				R = std::min<uint64_t>(n_chunks - 1, (uint64_t) (n_chunks * (raw_env / 100.0) + 0.5));
+			else {
+				climbing = true;
+				if (mt->raw_chunks_of != n_chunks) { // another text size: start from the model
+					mt->raw_chunks_of = n_chunks;
+					mt->raw_chunks = std::min<uint64_t>(r_max, (uint64_t) (n_chunks * host_raw_share_model(mt->packer->threads()) + 0.5));
+					mt->raw_calls = 0;
+					for (auto &t : mt->raw_time)
+						t = 0;
+				}
+				R = std::min<uint64_t>(mt->raw_chunks, r_max);
+			}
+		}
 		(void) cudaGetLastError();
 	}
 	const uint64_t n_raw = R * kPackChunk;
@@ -404,8 +421,10 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 			mt->d_raw = nullptr;
 			mt->raw_cap = 0;
 			mt->host_allocs++;
-			CU(cudaMalloc((void **) &mt->d_raw, n_raw + 64));
-			mt->raw_cap = n_raw + 64;
+			// room for the largest share the adaptation may reach (kMaxRawShare), so that a moving share never reallocates
+			const uint64_t want = std::max<uint64_t>(n_raw, ((uint64_t) (n_chunks * kMaxRawShare) + 1) * kPackChunk) + 64;
+			CU(cudaMalloc((void **) &mt->d_raw, want));
+			mt->raw_cap = want;
 		}
 		if (!mt->s_copy2) {
 			CU(cudaStreamCreateWithFlags(&mt->s_copy2, cudaStreamNonBlocking));
@@ -415,6 +434,8 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 		}
 		CU(cudaEventRecord(mt->ev_hyb[0], mt->s_copy2));
 	}
+	const double t_work = now(); // everything above may have allocated
+	const uint64_t allocs0 = mt->host_allocs;
 	pk.begin(text + n_raw, n - n_raw, kPackChunk, mt->h_pack_ring, slot_bytes, kPackRing);
 	for (uint64_t ci = 0; ci < R; ci++) { // the raw prefix: all copies and scans queued at once
 		const uint64_t b0 = ci * kPackChunk;
@@ -473,22 +494,29 @@ static int search_host_packed(acwm_matcher *mt, const uint8_t *text, uint64_t n,
 	const double t_issue = now();
 	rc = acwm_fetch(mt, count, positions, cap, n_written, mt->s_scan);
 	pk.finish();
-	if (R && raw_env < 0 && cudaStreamSynchronize(mt->s_copy) == cudaSuccess && cudaStreamSynchronize(mt->s_copy2) == cudaSuccess) {
-		// both sides started together: per chunk, the raw side took t_raw / R and the packed side t_pk / (n_chunks - R);
-		// they finish together at R* = n_chunks * b / (a + b) (a, b = time per raw / per packed chunk).  Half-way there.
-		float t_raw = 0, t_pk = 0;
-		if (cudaEventElapsedTime(&t_raw, mt->ev_hyb[0], mt->ev_hyb[1]) == cudaSuccess
-				&& cudaEventElapsedTime(&t_pk, mt->ev_hyb[2], mt->ev_hyb[3]) == cudaSuccess && t_raw > 0 && t_pk > 0) {
-			// the packed side is not done before its last chunk is packed and issued: the issue loop on the host clock
-			t_pk = std::max(t_pk, (float) ((t_issue - t_begin) * 1e3));
-			const double a = t_raw / (double) R, b = t_pk / (double) (n_chunks - R);
-			const double target = b / (a + b);
-			const double cur = (double) R / (double) n_chunks;
-			mt->raw_share = std::min(0.9, std::max(1.0 / (double) n_chunks, 0.5 * cur + 0.5 * target));
-			if (dbg)
-				fprintf(stderr, "  hybrid: %llu raw chunks %.3f ms, %llu packed chunks %.3f ms -> raw share %.2f\n", (unsigned long long) R,
-						t_raw, (unsigned long long) (n_chunks - R), t_pk, mt->raw_share);
-		}
+	if (climbing && (rc == ACWM_OK || rc == ACWM_ERR_OVERFLOW) && mt->host_allocs == allocs0) {
+		// this call's duration under its number of raw chunks; the next call: the best of R - 1, R, R + 1, a neighbour
+		// without a figure first, and every 16th call the neighbour whose figure is the oldest guess
+		const double t_call = now() - t_work;
+		double *T = mt->raw_time;
+		T[R] = T[R] > 0 ? 0.5 * T[R] + 0.5 * t_call : t_call;
+		uint64_t best = R; // the best point so far; its neighbours are what is worth knowing
+		for (uint64_t r = 0; r <= r_max; r++)
+			if (T[r] > 0 && T[r] < T[best])
+				best = r;
+		const uint64_t lo = best > 0 ? best - 1 : best, hi = std::min<uint64_t>(best + 1, r_max);
+		uint64_t next = best;
+		mt->raw_calls++;
+		if (T[hi] <= 0)
+			next = hi;
+		else if (T[lo] <= 0)
+			next = lo;
+		else if (mt->raw_calls % 16 == 0)
+			next = (mt->raw_calls / 16) % 2 ? hi : lo; // figures age: look at a neighbour again
+		mt->raw_chunks = next;
+		if (dbg)
+			fprintf(stderr, "  hybrid: %llu of %llu chunks raw: %.3f ms -> next %llu\n", (unsigned long long) R, (unsigned long long) n_chunks,
+					t_call * 1e3, (unsigned long long) next);
 	}
 	(void) cudaGetLastError();
 	double secs = 0;

@@ -67,6 +67,10 @@ struct acwm_matcher {
 	double host_rate[2] = {0, 0};             // [0] plain copy, [1] hybrid; 0 = not tried yet
 	uint32_t host_calls = 0;                  // measured calls
 	uint64_t host_allocs = 0;                 // device / pinned allocations made by the host-text paths (a call that allocates is not a measurement)
+	static constexpr int kRawTimes = 64;      // raw chunks the share may climb to (a 128 MiB text has 10 chunks)
+	uint64_t raw_chunks = 0, raw_chunks_of = 0; // chunks of a pinned text sent unpacked in the next hybrid transfer / of a text of so many chunks
+	uint32_t raw_calls = 0;
+	double raw_time[kRawTimes] = {};          // smoothed duration of the searches that ran with R raw chunks (0: none yet)
 	double raw_share = -1;                    // share of a pinned text sent unpacked, adapted from call to call (< 0: not yet measured)
 	std::vector<cudaEvent_t> ev_time;
 	std::array<cudaEvent_t, 2> ev_prof{};
