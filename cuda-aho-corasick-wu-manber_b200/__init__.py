@@ -57,7 +57,7 @@ class ScanParams(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in
                 ("algo", "packed2bit", "alphabet", "m_min", "m_max", "stride", "depth", "exact_front", "n_rows",
                  "f1_sh1", "f1_mult", "f1_sh2", "f1_words", "b2", "f2_mult", "f2_sh", "f2_words", "hb_mult",
-                 "hb_sh", "n_buckets", "n_entries", "n_classes", "r_mult", "r_sh", "r_entries", "r_entry_bytes", "r_in_smem", "f2_in_smem", "front_kind", "verify_kind", "v_rows", "ilp")]
+                 "hb_sh", "n_buckets", "n_entries", "n_classes", "r_mult", "r_sh", "r_entries", "r_entry_bytes", "r_in_smem", "f2_in_smem", "front_kind", "verify_kind", "v_rows", "ilp", "f1_k")]
 
 
 VENTRY_DTYPE = np.dtype([("key", "<u4"), ("len", "<u4"), ("offset", "<u8")])

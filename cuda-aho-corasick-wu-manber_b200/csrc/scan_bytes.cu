@@ -131,7 +131,7 @@ struct FrontWMB : BytesKey {
 	static constexpr int kExpand = S;
 	uint32_t bm_s;      // shared-memory block bitmap (shared address)
 	const uint32_t *bm; // global-memory block bitmap
-	uint32_t sh1, mult, sh2;
+	uint32_t sh1, mult, sh2, sh2b;
 	uint32_t hw[kWords];
 
 	TabRef rmk;
@@ -150,6 +150,7 @@ struct FrontWMB : BytesKey {
 		sh1 = a.prm.f1_sh1;
 		mult = a.prm.f1_mult;
 		sh2 = a.prm.f1_sh2;
+		sh2b = a.prm.f1_k == 2 ? sh2 - 5 : sh2; // where the entry's second bit comes from (one bit per entry: the same again)
 	}
 	static __device__ __forceinline__ uint32_t sym_of(int g, int b) { return (uint32_t) ((g * 32 + b) * S); }
 	__device__ __forceinline__ void begin(const ScanArgs &, uint32_t) {
@@ -175,9 +176,10 @@ struct FrontWMB : BytesKey {
 			const uint32_t lo = (bl & 3) ? __byte_perm(X[bl >> 2], X[(bl >> 2) + 1], 0x3210 + 0x1111 * (bl & 3)) : X[bl >> 2];
 			const uint32_t hi = (bh & 3) ? __byte_perm(X[bh >> 2], X[(bh >> 2) + 1], 0x3210 + 0x1111 * (bh & 3)) : X[bh >> 2];
 			const uint64_t blk = (((uint64_t) hi << 32) | lo) >> sh1;
-			const uint32_t idx = (uint32_t) (mix64(blk) * mult) >> sh2;
+			const uint32_t h = mix64(blk) * mult, idx = h >> sh2;
 			const uint32_t word = GLOBAL ? __ldg(bm + (idx >> 5)) : lds32(bm_s + ((idx >> 3) & ~3u));
-			hw[j / 32] = __funnelshift_r(hw[j / 32], word >> (idx & 31), 1); // the sample's bit enters from the top
+			// blocked Bloom filter: both bits of an entry sit in one word
+			hw[j / 32] = __funnelshift_r(hw[j / 32], (word >> (idx & 31)) & (word >> ((h >> sh2b) & 31)), 1); // the sample's bit enters from the top
 		}
 	}
 	ACWM_SCAN_GROUPS()

@@ -321,7 +321,7 @@ struct FrontWM : PackedKey {
 	uint32_t bm_s;      // shared-memory block bitmap (shared address)
 	const uint32_t *bm; // global-memory block bitmap
 	TabRef rmk;         // offset masks
-	uint32_t sh1, mult, sh2;
+	uint32_t sh1, mult, sh2, sh2b;
 	uint32_t W[8];
 	uint32_t hw[kWords];
 
@@ -332,6 +332,7 @@ struct FrontWM : PackedKey {
 		sh1 = a.prm.f1_sh1;
 		mult = a.prm.f1_mult;
 		sh2 = a.prm.f1_sh2;
+		sh2b = a.prm.f1_k == 2 ? sh2 - 5 : sh2; // hashed bitmaps: where the entry's second bit comes from (one bit: the same again)
 	}
 	static __device__ __forceinline__ uint32_t sym_of(int g, int b) { return (uint32_t) ((g * 32 + b) * S); }
 
@@ -358,11 +359,16 @@ struct FrontWM : PackedKey {
 			const int bit = 2 * (j * S) + 2;
 			const int wi = bit >> 5, sh = bit & 31;
 			const uint32_t v = sh ? __funnelshift_r(W[wi], W[wi + 1], sh) : W[wi];
-			uint32_t idx = v >> sh1;
-			if (MODE != 0)
-				idx = (idx * mult) >> sh2;
+			uint32_t idx = v >> sh1, h = 0;
+			if (MODE != 0) {
+				h = idx * mult;
+				idx = h >> sh2;
+			}
 			const uint32_t word = MODE == 2 ? __ldg(bm + (idx >> 5)) : lds32(bm_s + ((idx >> 3) & ~3u));
-			hw[j / 32] = __funnelshift_r(hw[j / 32], word >> (idx & 31), 1); // the sample's bit enters from the top
+			uint32_t t = word >> (idx & 31);
+			if (MODE != 0) // blocked Bloom filter: the entry's second bit sits in the same word
+				t &= word >> ((h >> sh2b) & 31);
+			hw[j / 32] = __funnelshift_r(hw[j / 32], t, 1); // the sample's bit enters from the top
 		}
 		constexpr int r = kSamples % 32; // the last word holds fewer than 32 samples: bring them down to bit 0
 		if constexpr (r != 0)

@@ -496,6 +496,7 @@ static int compile_ac_bytes(const PatternSet &ps, const acwm_options &opts, uint
 // e is covered by the sample c = e - r, r = e mod-aligned distance < s, because
 // B <= m_min - s + 1 keeps the block inside the occurrence.
 // Where a WM stage-1 bitmap for stride s would live and how selective it would be.
+constexpr double kBloom2MaxLoad = 0.4; // entries per bit below which two bits per entry beat one
 struct WmPlan {
 	uint32_t s = 0, B = 0, fbits = 0;
 	bool direct = false, in_smem = true;
@@ -513,7 +514,8 @@ static WmPlan plan_wm_stride(const PatternSet &ps, bool packed, uint32_t s, uint
 		// a sample is a candidate with probability `rate` and then costs its lane ~60 slots (the rest of the
 		// warp waits) plus ~40 per offset it has to probe: about `load` offsets, at most s
 		const double load = entries / std::pow(2.0, (double) std::min(fbits, key_bits));
-		const double rate = 1.0 - std::exp(-load);
+		// a hashed bitmap with room to spare sets two bits per entry (see compile_wm): far fewer false candidates
+		const double rate = (!direct && load < kBloom2MaxLoad) ? std::pow(1.0 - std::exp(-2.0 * load), 2.0) : 1.0 - std::exp(-load);
 		// per symbol: ~8 lane-instructions per sample (+16 when the bitmap word comes from L2: measured on
 		// BASELINE config 4, profiles/r01g_tune.csv)
 		const double cost = ((packed ? 8.0 : 10.0) + (in_smem ? 0.0 : 16.0) + rate * 60.0
@@ -588,6 +590,10 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 	}
 	prm.f1_sh1 = packed ? 32 - 2 * B : 64 - 8 * B; // drop symbols older than the block
 	prm.f1_words = (uint32_t) (((uint64_t) 1 << fbits) / 32);
+	// Hashed bitmaps (every candidate of a random text is a hash collision there): while the bitmap has room, an entry
+	// sets TWO bits of its word -- bit (h >> sh2) & 31 and bit (h >> (sh2 - 5)) & 31 of word h >> (sh2 + 5), h = block *
+	// mult: a blocked Bloom filter, one load per sample as before, false candidates ~ (2 load)^2 instead of load
+	prm.f1_k = (!plan.direct && (double) s * pd / std::pow(2.0, (double) fbits) < kBloom2MaxLoad && prm.f1_sh2 >= 5) ? 2 : 1;
 	std::vector<uint32_t> bm(prm.f1_words, 0);
 	for (uint32_t j = 0; j < pd; j++)
 		for (uint32_t r = 0; r < s; r++) {
@@ -596,7 +602,10 @@ static int compile_wm(const PatternSet &ps, const acwm_options &opts, bool packe
 				v = pack2_tail(ps.pat(j), ps.len[j], B, r);
 			else
 				v = mix64to32(pack8_tail(ps.pat(j), ps.len[j], B, r));
-			set_bit(bm, (uint32_t) (v * prm.f1_mult) >> prm.f1_sh2);
+			const uint32_t h = v * prm.f1_mult, idx = h >> prm.f1_sh2;
+			set_bit(bm, idx);
+			if (prm.f1_k == 2)
+				set_bit(bm, (idx & ~31u) | ((h >> (prm.f1_sh2 - 5)) & 31u));
 		}
 	c.front_entry_bytes = 4;
 	c.front.resize((size_t) prm.f1_words * 4);

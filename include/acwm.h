@@ -308,6 +308,8 @@ typedef struct acwm_scan_params {
 	uint32_t verify_kind;   /* what decides a candidate window: 0 = hash buckets + compare, 1 = walk of the verify DFA */
 	uint32_t v_rows;        /* rows of the verify DFA (ACWM_BLOB_VDFA) */
 	uint32_t ilp;           /* AC, exact K = 3 automaton in shared memory: 2 = every lane walks its chunk as two independent chains */
+	uint32_t f1_k;          /* WM stage 1, hashed bitmaps: bits per entry (1, or 2 = blocked Bloom filter: both bits in the word
+	                         * idx >> 5, the second at bit ((v >> sh1) * mult >> (sh2 - 5)) & 31) */
 } acwm_scan_params;
 
 /* ------------------- reference-shaped shims (smatcher.h) ------------------- */

@@ -177,9 +177,13 @@ class Emulator:
                 cin = cpos[cpos < n]
                 v = np.zeros(cpos.size, np.uint64)
                 v[:cin.size] = win[cin]
-                idx = _mul32(v >> np.uint64(p.f1_sh1), p.f1_mult) >> np.uint64(p.f1_sh2)
+                h = _mul32(v >> np.uint64(p.f1_sh1), p.f1_mult)
+                idx = h >> np.uint64(p.f1_sh2)
                 bm = self.front.view(np.uint32)
-                bit = (bm[(idx >> np.uint64(5)).astype(np.int64)] >> (idx & np.uint64(31)).astype(np.uint32)) & 1
+                word = bm[(idx >> np.uint64(5)).astype(np.int64)]
+                bit = (word >> (idx & np.uint64(31)).astype(np.uint32)) & 1
+                if p.f1_k == 2:  # blocked Bloom filter: the entry's second bit in the same word
+                    bit &= (word >> ((h >> np.uint64(p.f1_sh2 - 5)) & np.uint64(31)).astype(np.uint32)) & 1
                 ends = self._expand(cpos[bit == 1], (v >> np.uint64(p.f1_sh1))[bit == 1], s, n)
             keys = win[ends] >> np.uint64(32 - 2 * p.b2)
         else:
@@ -197,9 +201,13 @@ class Emulator:
                 s = p.stride
                 cpos = np.arange(0, n, s, dtype=np.int64)
                 blk = win[cpos] >> np.uint64(p.f1_sh1)
-                idx = _mul32(_mix64(blk), p.f1_mult) >> np.uint64(p.f1_sh2)
+                h = _mul32(_mix64(blk), p.f1_mult)
+                idx = h >> np.uint64(p.f1_sh2)
                 bm = self.front.view(np.uint32)
-                bit = (bm[(idx >> np.uint64(5)).astype(np.int64)] >> (idx & np.uint64(31)).astype(np.uint32)) & 1
+                word = bm[(idx >> np.uint64(5)).astype(np.int64)]
+                bit = (word >> (idx & np.uint64(31)).astype(np.uint32)) & 1
+                if p.f1_k == 2:
+                    bit &= (word >> ((h >> np.uint64(p.f1_sh2 - 5)) & np.uint64(31)).astype(np.uint32)) & 1
                 ends = self._expand(cpos[bit == 1], _mix64(blk)[bit == 1], s, n)
             keys = _mix64(win[ends] >> np.uint64(64 - 8 * p.b2))
         res = self._verify(text, ends, keys)

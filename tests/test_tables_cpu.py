@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(acwm):
 
 
 def test_struct_sizes(acwm):
-    assert C.sizeof(acwm.Options) == 44 and C.sizeof(acwm.Info) == 80 and C.sizeof(acwm.ScanParams) == 128
+    assert C.sizeof(acwm.Options) == 44 and C.sizeof(acwm.Info) == 80 and C.sizeof(acwm.ScanParams) == 132
     assert acwm.VENTRY_DTYPE.itemsize == 16
 
 
