@@ -567,9 +567,18 @@ int acwm_build(int algo, const uint8_t *patterns, const uint32_t *lens, uint32_t
 	if (opts)
 		mt->opts = *opts;
 	std::string err;
-	int rc = normalize_patterns(patterns, lens, m, p, alphabet, mt->ps, err);
-	if (rc == ACWM_OK)
-		rc = compile_tables(algo, mt->ps, mt->opts, mt->c, err);
+	int rc;
+	try { // the table compiler grows std::vectors: no exception leaves the C ABI
+		rc = normalize_patterns(patterns, lens, m, p, alphabet, mt->ps, err);
+		if (rc == ACWM_OK)
+			rc = compile_tables(algo, mt->ps, mt->opts, mt->c, err);
+	} catch (const std::bad_alloc &) {
+		rc = ACWM_ERR_NOMEM;
+		err = "host allocation failed while compiling the tables";
+	} catch (const std::exception &e) {
+		rc = ACWM_ERR_INVALID;
+		err = std::string("table compiler: ") + e.what();
+	}
 	if (rc != ACWM_OK) {
 		delete mt;
 		return set_error(rc, err);

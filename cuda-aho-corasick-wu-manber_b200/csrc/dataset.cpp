@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <new>
 #include <vector>
 
 #include "../../include/acwm.h"
@@ -132,8 +133,13 @@ int acwm_load_text(const char *path, uint32_t alphabet, uint64_t max_symbols, ui
 	std::vector<uint8_t> raw;
 	uint8_t buf[1 << 16];
 	size_t got;
-	while ((got = fread(buf, 1, sizeof(buf), f)) > 0)
-		raw.insert(raw.end(), buf, buf + got);
+	try { // no exception leaves the C ABI
+		while ((got = fread(buf, 1, sizeof(buf), f)) > 0)
+			raw.insert(raw.end(), buf, buf + got);
+	} catch (const std::bad_alloc &) {
+		fclose(f);
+		return set_error(ACWM_ERR_NOMEM, "host allocation failed while reading the corpus");
+	}
 	fclose(f);
 	uint8_t *out = (uint8_t *) malloc(raw.size() + 1);
 	if (!out)

@@ -172,14 +172,18 @@ bool HostPacker::pack_one(const Job &j) {
 		const uint64_t c = p / j.ppc;
 		if (c >= gate_.load(std::memory_order_acquire))
 			return false;
-		if (!ticket_.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel))
+		inflight_.fetch_add(1, std::memory_order_acq_rel); // before the claim: finish() never sees a claimed piece it does not wait for
+		if (!ticket_.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel)) {
+			inflight_.fetch_sub(1, std::memory_order_acq_rel);
 			continue;
+		}
 		const uint64_t lo = p * kPiece, hi = lo + kPiece < j.n ? lo + kPiece : j.n;
 		uint8_t *dst = j.ring + (c % j.ring_chunks) * j.slot_bytes + (p % j.ppc) * (kPiece / 4);
 		const uint64_t bad = fn(j.src + lo, dst, hi - lo);
 		if (bad)
 			bad_.fetch_or(bad, std::memory_order_relaxed);
 		done_[c % kMaxRing].fetch_add(1, std::memory_order_release);
+		inflight_.fetch_sub(1, std::memory_order_acq_rel);
 		return true;
 	}
 }
@@ -235,7 +239,15 @@ void HostPacker::begin(const uint8_t *src, uint64_t n_sym, uint64_t chunk_sym, u
 		cv_.notify_all();
 }
 
-void HostPacker::finish() { active_.store(false, std::memory_order_release); }
+// End of a job, also on an error path of the caller with pieces still unclaimed: the ticket is voided (no worker claims
+// another piece of this job, none spins on its gated pieces), and the pieces in flight are waited for -- when finish()
+// returns nobody reads the caller's text or writes the ring any more.
+void HostPacker::finish() {
+	ticket_.store(~0ull, std::memory_order_release);
+	while (inflight_.load(std::memory_order_acquire))
+		std::this_thread::yield();
+	active_.store(false, std::memory_order_release);
+}
 
 bool HostPacker::chunk_ready(uint64_t c) const {
 	const uint64_t first = c * cur_.ppc, last = first + cur_.ppc < cur_.pieces ? first + cur_.ppc : cur_.pieces;

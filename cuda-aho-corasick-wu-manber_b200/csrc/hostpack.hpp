@@ -58,6 +58,7 @@ private:
 	bool quit_ = false;
 	Job job_, cur_;
 	std::atomic<uint64_t> ticket_{0}, gate_{0}, bad_{0}, seq_{0};
+	std::atomic<uint32_t> inflight_{0}; // pieces claimed and not yet written: finish() waits for them
 	std::atomic<bool> active_{false};
 	std::array<std::atomic<uint64_t>, kMaxRing> done_{};
 };

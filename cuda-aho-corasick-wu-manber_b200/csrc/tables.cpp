@@ -437,7 +437,9 @@ static int compile_ac_bytes(const PatternSet &ps, const acwm_options &opts, uint
 		d_hi = m; // also try the exact automaton
 	if (opts.force_depth)
 		d_lo = d_hi = std::min<uint32_t>(std::max<uint32_t>(opts.force_depth, 1), Dmax);
-	const uint32_t max_rows_global = 1u << 22;
+	// rows are bounded by the 2^31-byte table limit below BEFORE the trie is built: a byte-alphabet trie costs 4 * ncols
+	// bytes per node, so an unbounded one could take GiBs per depth tried
+	const uint32_t max_rows_global = (uint32_t) std::min<uint64_t>(1u << 22, (1ull << 31) / (4ull * ncols));
 	for (uint32_t D = d_hi; D >= d_lo; D--) {
 		if (D > 8 && D != m && !opts.force_depth)
 			continue;
@@ -447,6 +449,8 @@ static int compile_ac_bytes(const PatternSet &ps, const acwm_options &opts, uint
 			continue;
 		const bool exact = (D == m);
 		const double rate = exact ? 0.0 : std::min(1.0, (double) t.leaves / std::pow((double) ps.alphabet, (double) D));
+		if (!exact && rate > 0.25 && D < d_hi && !opts.force_depth)
+			continue; // a front that lets a quarter of the positions through filters nothing: the divergent verify path would run the scan
 		const uint64_t smem_bytes = (uint64_t) t.rows * ncols * 2;
 		const bool fits = smem_bytes <= budget && t.rows < (1u << 15);
 		// one lookup per symbol: ~8 lane-instructions from shared memory, ~40 from L2
