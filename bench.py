@@ -271,9 +271,10 @@ def measure_pinned_copy(torch, dev, nbytes=128 << 20, window_s=0.3):
     t0 = time.perf_counter()
     copies = 0
     while time.perf_counter() - t0 < window_s:
-        dst.copy_(src, non_blocking=True)
+        for _ in range(4):  # back to back: the DMA engine never waits for the host
+            dst.copy_(src, non_blocking=True)
         torch.cuda.synchronize()
-        copies += 1
+        copies += 4
     return copies * nbytes / (time.perf_counter() - t0) / 1e9
 
 

@@ -109,6 +109,7 @@ struct FrontAC : PackedKey {
 	const uint8_t *tab; // global-memory DFA
 	uint32_t ent;       // current entry (byte offset of the row | hits)
 	uint32_t nwu, hist; // warm-up strides / symbols of history they (and the first in-chunk stride) cover
+	uint32_t nwb;       // warm-up strides of the second chain
 	uint32_t W[8];      // W[0] = the 16 symbols in front of the chunk, W[1..7] = the chunk
 	uint32_t H[3];      // long warm-up only: symbols -64..-17
 	uint32_t hw[kWords];
@@ -119,10 +120,8 @@ struct FrontAC : PackedKey {
 		// the state must have seen depth-1 symbols of history when the chunk starts; the first
 		// in-chunk stride covers kOff of them
 		const uint32_t need = a.prm.depth - 1;
-		if (ILP == 2) // both chains warm up over the same whole strides (the host picks two chains for depth <= 13: 4 strides)
-			nwu = (need + K - 1) / K;
-		else
-			nwu = need > (uint32_t) kOff ? (need - kOff + K - 1) / K : 0u;
+		nwu = need > (uint32_t) kOff ? (need - kOff + K - 1) / K : 0u;
+		nwb = (need + K - 1) / K; // chain B starts on a stride boundary: whole strides of history (the host picks two chains for depth <= 13: 4 strides)
 		hist = kOff + K * nwu; // <= 16: W[0] is enough; else up to 64 symbols of raw history
 	}
 	// bit b of hit word g = a hit at this chunk symbol (bits of symbols in front of the chunk are cleared by walk())
@@ -219,15 +218,18 @@ struct FrontAC : PackedKey {
 			static_assert(wb >= 1, "chain B's history lies in the chunk");
 			uint32_t ha = W[0] << (2 * kOff);                                           // stream bits [-2 kOff, 32 - 2 kOff)
 			uint32_t hb = sb ? __funnelshift_r(W[wb - 1], W[wb], sb) : W[wb - 1];       // stream bits [bitB - 32, bitB)
-			const uint32_t sh = 32 - 2 * K * nwu - kSS; // the warm-up symbols, oldest first, at bit kSS
-			ha >>= sh;
-			hb >>= sh;
+			// the warm-up symbols, oldest first, at bit kSS; chain A's first in-chunk stride already covers kOff symbols of
+			// history, so it may need one warm-up stride less than chain B and sits out the first round(s) of the loop
+			ha >>= 32 - 2 * K * nwu - kSS;
+			hb >>= 32 - 2 * K * nwb - kSS;
 			uint32_t eb = 0;
 #pragma unroll 1
-			for (uint32_t i = 0; i < nwu; i++) {
-				step_of(ent, ha);
+			for (uint32_t i = 0; i < nwb; i++) {
+				if (i + nwu >= nwb) {
+					step_of(ent, ha);
+					ha >>= 2 * K;
+				}
 				step_of(eb, hb);
-				ha >>= 2 * K;
 				hb >>= 2 * K;
 			}
 			two_chains<0, kLen0>(ent, eb);
