@@ -518,10 +518,11 @@ def run_ours(args):
     link = measure_pinned_copy(torch, rig.dev)
     _, links = rig.max_over_ranks(link)
 
-    # ---- the sizes the north star scales on: 1 GiB of DNA per GPU for both algorithms, configs[2] at 10^9 B per GPU
+    # ---- the sizes the north star scales on: 1 GiB of DNA per GPU for both algorithms, configs[2] at 10^9 B per GPU,
+    # configs[3] (bytes, 10 000 mixed-length patterns) at its full 2 * 10^9 B per GPU
     big = []
     if not args.no_big_legs and args.workload == DEFAULT_WORKLOAD:
-        for wl, nb in (("c1", 1 << 30), ("c2", 1 << 30), ("c3", 10 ** 9)):
+        for wl, nb in (("c1", 1 << 30), ("c2", 1 << 30), ("c3", 10 ** 9), ("c4", 2 * 10 ** 9)):
             rep = run_leg(rig, wl, nb, max(5, args.steps // 5), 3, full=False)
             big.append({k: rep[k] for k in ("workload", "algo", "text_bytes_per_gpu", "value", "unit", "ms_per_step",
                                             "gpu_launches", "matches_last_step", "roofline", "kernel", "count_exchange",

@@ -656,3 +656,25 @@ print("DONE")
     env = dict(__import__("os").environ, ACWM_TUNE="0x0303")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env).stdout
     assert "DONE" in out and "ERROR %d" % acwm.ERR_CUDA in out and "position ordering gave up" in out, out
+
+
+def test_host_search_stays_exact_while_it_adapts(acwm, oracle, torch_cuda):
+    """acwm_search_host measures its hybrid and its plain transfer on its first calls, keeps the faster, and lets the raw
+    share of the hybrid one climb on the measured call times: every one of those calls returns the oracle's matches
+    (pinned text, so the hybrid path is open; the text changes from call to call)."""
+    torch = torch_cuda
+    dg = __import__("acwm_pkg").submodule("datagen")
+    n = 96 << 20  # 7 chunks: enough for the hybrid split
+    texts = [dg.text_host(n, 4, 40 + k) for k in range(2)]
+    pats = dg.patterns_with_hits(texts[0], 200, 12, 4, 9)
+    refs = [oracle.set_search(pats, t) for t in texts]
+    pinned = [torch.from_numpy(t).pin_memory() for t in texts]
+    mt = acwm.Matcher(acwm.WM, pats, 4)
+    h2d = set()
+    for i in range(14):
+        count, pos = mt.search_host(pinned[i % 2], cap=max(1024, refs[i % 2]["count"]))
+        assert count == refs[i % 2]["count"], i
+        assert np.array_equal(pos, refs[i % 2]["positions"]), i
+        h2d.add(int(mt.last_h2d_bytes))
+    assert len(h2d) >= 2  # both transfers (and more than one split) were exercised
+    mt.close()
