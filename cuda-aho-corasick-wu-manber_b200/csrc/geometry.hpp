@@ -1,9 +1,9 @@
 // Tile geometry shared by the table compiler (shared-memory budgeting) and the kernels.
 //
-// One persistent CTA per SM; every WARP owns whole tiles of the text and double- or
-// triple-buffers them RAW (one byte per symbol, as the reference stores the text) in
-// shared memory, filled by one TMA bulk copy per tile.  A lane reads its 112-byte
-// chunk with 7 LDS.128: lane stride 112 B = 16 B * 7 (odd) -> conflict-free.
+// Persistent CTAs (one full-size or two half-size ones per SM); every WARP owns whole tiles of the text and keeps
+// them RAW (one byte per symbol, as the reference stores the text) in one or two slots of shared memory, each filled
+// by one TMA bulk copy per tile.  A lane reads its 112-byte chunk with 7 LDS.128: lane stride 112 B = 16 B * 7
+// (odd) -> conflict-free.
 #pragma once
 #include <cstdint>
 
@@ -46,8 +46,8 @@ constexpr uint32_t kStageBlock = 1u << kStageBlockLog2; // staging slots of a wa
 
 // (warps, stages, CTAs per SM) the scan kernel is launched with, in order of preference.  The 2-bit path
 // copies a tile into registers first and refills its slot while it walks, so one slot per
-// warp already overlaps load and scan; the bytes path reads the raw tile throughout and needs two.  The ring
-// depth is a compile-time constant of the kernels (1 / 2).
+// warp already overlaps load and scan; the bytes path reads the raw tile throughout: two slots, or one and more
+// warps.  The ring depth is a template parameter of the kernels (1 / 2).
 struct LaunchShape {
 	uint32_t warps, stages, ctas;
 };

@@ -3,7 +3,7 @@
 // ONE launch does the whole job -- supersedes the reference's kernel + D2H of 7680 per-thread
 // counters + host sum (cuda/cuda_ac.cu:654-673) -- and no CTA ever waits for the whole grid:
 //
-//   1. scan     one persistent CTA per SM owns a contiguous span of warp tiles; every warp
+//   1. scan     every persistent CTA (one or two per SM) owns a contiguous span of warp tiles; every warp
 //               runs its own TMA pipeline over the span (cp.async.bulk global -> shared,
 //               mbarrier complete_tx, no block-wide barrier), walks its front end over the tile,
 //               checks the candidates (warp-cooperatively when they are few) and stages each match as
