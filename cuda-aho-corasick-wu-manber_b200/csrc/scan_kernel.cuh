@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 	// tile0 + t * tile_stride (load_bytes bytes: history + tile)
 	const bool packed_in = kPacked && a.packed_in;
 	const uint32_t int_hi = (uint32_t) ((packed_in ? ((a.data_hi + 63) & ~(uint64_t) 63) : (a.data_hi & ~(uint64_t) 15)) / kTile);
+	const uint32_t int_span = int_hi ? int_hi - 1u : 0u; // number of interior tiles
 	const uint32_t tile_stride = packed_in ? kTile / 4 : kTile, load_bytes = packed_in ? kLoadBytes / 4 : kLoadBytes;
 	const uint8_t *tile0 = a.text16 - (packed_in ? kHalo / 4 : kHalo);
 	const uint32_t cta_lo32 = (uint32_t) cta_lo; // tile numbers fit 28 bits (staging entries)
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const __grid_consta
 		if (idx >= n_b)
 			return;
 		const uint32_t t = cta_lo32 + idx;
-		if (t - 1u < int_hi - 1u) { // 1 <= t < int_hi (int_hi = 0: never)
+		if (t - 1u < int_span) { // 1 <= t < int_hi, one unsigned compare
 			if (lane == 0) {
 				mbar_expect_tx(slot_bar[s], load_bytes);
 				tma_bulk_g2s(slot_buf[s], tile0 + (uint64_t) t * tile_stride, load_bytes, slot_bar[s], kPolicyEvictFirst);
