@@ -747,13 +747,13 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 		// Packing pays when the cores out-run what the link carries raw (a core packs 5-7 GB/s, one PCIe link moves
 		// ~55 GB/s of raw text) -- and when the box has the memory bandwidth for both: the first searches run the hybrid
 		// transfer, then the plain copy (one call each to set up, one to measure), and from then on the faster of the
-		// two runs (the other is re-tried every 32nd call).
+		// two runs (the other is re-tried every 16th call).
 		if (pack_mode == 2)
 			return search_host_packed(mt, text, n, count, positions, cap, n_written, want_positions);
 		if (mt->packer->threads() >= kHostPackMinThreads) {
 			// a call that had to allocate (the first of either kind, a longer text) does not count as a measurement
 			int mode = mt->host_rate[1] <= 0 ? 1 : mt->host_rate[0] <= 0 ? 0 : (mt->host_rate[1] >= mt->host_rate[0] ? 1 : 0);
-			if (mt->host_rate[0] > 0 && mt->host_rate[1] > 0 && mt->host_calls % 32 == 31)
+			if (mt->host_rate[0] > 0 && mt->host_rate[1] > 0 && mt->host_calls % 16 == 15)
 				mode ^= 1;
 			const uint64_t allocs = mt->host_allocs;
 			timespec t0, t1;
@@ -763,8 +763,9 @@ int acwm_search_host(acwm_matcher *mt, const uint8_t *text, uint64_t n, uint64_t
 			clock_gettime(CLOCK_MONOTONIC, &t1);
 			const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 			if ((rc == ACWM_OK || rc == ACWM_ERR_OVERFLOW) && secs > 0 && mt->host_allocs == allocs) {
+				// the plain copy is one thing (smoothed); the hybrid transfer changes as its raw share climbs: its last call counts
 				const double rate = (double) n / secs;
-				mt->host_rate[mode] = mt->host_rate[mode] > 0 ? 0.5 * mt->host_rate[mode] + 0.5 * rate : rate;
+				mt->host_rate[mode] = (mode == 0 && mt->host_rate[0] > 0) ? 0.5 * mt->host_rate[0] + 0.5 * rate : rate;
 				mt->host_calls++;
 			}
 			return rc;
